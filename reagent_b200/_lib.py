@@ -1,0 +1,142 @@
+"""ctypes binding of libreagent_b200.so (the C ABI in include/reagent_b200.h).
+
+The product path has NO fallback: if the CUDA library is missing or a call fails this
+module raises.  Build with `python -c "import __graft_entry__ as g; g.build()"` or
+`reagent_b200/csrc/build.sh`.
+"""
+import ctypes as C
+import os
+
+MAX_LAYERS = 8
+
+ACT = {"linear": 0, "relu": 1, "tanh": 2, "leaky_relu": 3, "sigmoid": 4, "softplus": 5}
+LOSS_MSE, LOSS_HUBER = 0, 1
+DISCOUNT_CONST, DISCOUNT_POW = 0, 1
+
+_f32p = C.POINTER(C.c_float)
+_vp = C.c_void_p
+
+
+class MlpT(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_int32),
+        ("dims", C.c_int32 * (MAX_LAYERS + 1)),
+        ("act", C.c_int32 * MAX_LAYERS),
+        ("params", _vp),
+        ("w_off", C.c_int64 * MAX_LAYERS),
+        ("b_off", C.c_int64 * MAX_LAYERS),
+        ("n_params", C.c_int64),
+    ]
+
+
+class NetWsT(C.Structure):
+    _fields_ = [
+        ("hidden", _vp * MAX_LAYERS),
+        ("dz", _vp * MAX_LAYERS),
+        ("input", _vp),
+    ]
+
+
+class DqnArgsT(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32),
+        ("state", _vp),
+        ("next_state", _vp),
+        ("action", _vp),
+        ("next_action", _vp),
+        ("reward", _vp),
+        ("not_terminal", _vp),
+        ("possible_next_actions_mask", _vp),
+        ("discount_src", _vp),
+        ("reward_boost", _vp),
+        ("gamma", C.c_float),
+        ("discount_mode", C.c_int32),
+        ("double_q", C.c_int32),
+        ("maxq", C.c_int32),
+        ("loss_kind", C.c_int32),
+        ("do_backward", C.c_int32),
+        ("all_action_scores", _vp),
+        ("td_target", _vp),
+        ("q_selected", _vp),
+        ("next_action_idx", _vp),
+        ("loss_partials", _vp),
+        ("loss", _vp),
+        ("tile_counter", _vp),
+    ]
+
+
+class AdamArgsT(C.Structure):
+    _fields_ = [
+        ("params", _vp),
+        ("grad", _vp),
+        ("splits", C.c_int32),
+        ("n", C.c_int64),
+        ("exp_avg", _vp),
+        ("exp_avg_sq", _vp),
+        ("step", _vp),
+        ("block_counter", _vp),
+        ("lr", C.c_double),
+        ("beta1", C.c_double),
+        ("beta2", C.c_double),
+        ("eps", C.c_double),
+        ("weight_decay", C.c_double),
+        ("grad_scale", C.c_float),
+        ("target", _vp),
+        ("tau", C.c_float),
+        ("one_minus_tau", C.c_float),
+    ]
+
+
+class Rb200Error(RuntimeError):
+    pass
+
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libreagent_b200.so")
+
+
+def _declare(lib):
+    lib.rb200_last_error.restype = C.c_char_p
+    lib.rb200_version.restype = C.c_int
+    lib.rb200_device_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.rb200_num_row_tiles.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.rb200_dqn_td_step.argtypes = [C.POINTER(MlpT), C.POINTER(MlpT), C.POINTER(DqnArgsT),
+                                      C.POINTER(NetWsT), _vp]
+    lib.rb200_mlp_forward.argtypes = [C.POINTER(MlpT), _vp, C.c_int32, _vp, C.c_int32, C.c_int32,
+                                      _vp, _vp]
+    lib.rb200_wgrad_splits.argtypes = [C.c_int]
+    lib.rb200_mlp_wgrad.argtypes = [C.POINTER(MlpT), _vp, C.c_int32, C.POINTER(NetWsT), _vp,
+                                    C.c_int32, _vp]
+    lib.rb200_grad_reduce.argtypes = [_vp, C.c_int32, C.c_int64, _vp, _vp]
+    lib.rb200_adam_soft_update.argtypes = [C.POINTER(AdamArgsT), _vp]
+    lib.rb200_soft_update.argtypes = [_vp, _vp, C.c_int64, C.c_float, C.c_float, _vp]
+
+
+def lib():
+    """Load (once) and return the shared library; raise loudly if it is missing."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise Rb200Error(
+                f"{LIB_PATH} not found: the CUDA extension is not built. "
+                "Run reagent_b200/csrc/build.sh (there is no CPU fallback).")
+        _LIB = C.CDLL(LIB_PATH)
+        _declare(_LIB)
+    return _LIB
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().rb200_last_error().decode("utf-8", "replace")
+        raise Rb200Error(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def cur_stream():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,304 @@
+// reagent_b200 -- weight-gradient, gradient-reduce, fused Adam + soft-update kernels (K3).
+#include <math.h>
+
+#include "rb200_common.cuh"
+
+namespace rb200 {
+
+// ---------------------------------------------------------------------------
+// dW_l[n,k] = sum_b dZ_l[b,n] * A_{l-1}[b,k];  db_l[n] = sum_b dZ_l[b,n]
+// One CTA = one 64(n) x 64(k) tile of one layer over one batch split.
+// 256 threads, each 4(n) x 4(k) outputs; per batch row a thread issues 2 LDS.128
+// (dz quad broadcast across the 16 threads that share it, a quad conflict-free)
+// for 16 FMAs.  Deterministic: partial s of the split-K sum goes to its own slab.
+// ---------------------------------------------------------------------------
+constexpr int kWgTile = 64;
+constexpr int kWgRows = 32;  // batch rows staged per step
+
+struct WgradLayer {
+  const float* A;   // [B, K] input activations of this layer
+  const float* dZ;  // [B, N] pre-activation gradients of this layer
+  int K, N;
+  long long w_off, b_off;
+  int tiles_n, tiles_k, tile_start;
+};
+struct WgradParams {
+  int n_layers;
+  WgradLayer L[kMaxLayers];
+  int B, splits, rows_per_split;
+  float* gpart;
+  long long P;
+};
+
+__global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradParams p) {
+  __shared__ __align__(16) float zs[2][kWgRows][kWgTile + 4];
+  __shared__ __align__(16) float as[2][kWgRows][kWgTile + 4];
+  int li = 0;
+  while (li + 1 < p.n_layers && (int)blockIdx.x >= p.L[li + 1].tile_start) ++li;
+  const WgradLayer& Ly = p.L[li];
+  const int t = blockIdx.x - Ly.tile_start;
+  const int tn = t / Ly.tiles_k, tk = t - tn * Ly.tiles_k;
+  const int n0 = tn * kWgTile, k0 = tk * kWgTile;
+  const int split = blockIdx.y;
+  const int b_begin = split * p.rows_per_split;
+  const int b_end = min(p.B, b_begin + p.rows_per_split);
+  const int tid = threadIdx.x;
+  const int in_ = tid >> 4, ik = tid & 15;  // thread owns n = n0+4*in_.., k = k0+4*ik..
+  const int N = Ly.N, K = Ly.K;
+  const bool vz = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(Ly.dZ) & 15) == 0);
+  const bool va = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(Ly.A) & 15) == 0);
+
+  float acc[4][4];
+  float bsum[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bsum[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  }
+
+  auto stage = [&](int b0, int buf) {
+    // 32 rows x 16 quads for each operand = 512 quads each; 256 threads -> 2 + 2
+    for (int idx = tid; idx < kWgRows * 16; idx += kThreads) {
+      const int r = idx >> 4, qd = idx & 15;
+      const int b = b0 + r;
+      {
+        const int n = n0 + 4 * qd;
+        float* d = &zs[buf][r][4 * qd];
+        if (b < b_end && vz && n + 3 < N) {
+          cp_async16(d, Ly.dZ + (size_t)b * N + n);
+        } else {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (b < b_end) {
+            const float* s = Ly.dZ + (size_t)b * N;
+            if (n < N) v.x = s[n];
+            if (n + 1 < N) v.y = s[n + 1];
+            if (n + 2 < N) v.z = s[n + 2];
+            if (n + 3 < N) v.w = s[n + 3];
+          }
+          *reinterpret_cast<float4*>(d) = v;
+        }
+      }
+      {
+        const int k = k0 + 4 * qd;
+        float* d = &as[buf][r][4 * qd];
+        if (b < b_end && va && k + 3 < K) {
+          cp_async16(d, Ly.A + (size_t)b * K + k);
+        } else {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (b < b_end) {
+            const float* s = Ly.A + (size_t)b * K;
+            if (k < K) v.x = s[k];
+            if (k + 1 < K) v.y = s[k + 1];
+            if (k + 2 < K) v.z = s[k + 2];
+            if (k + 3 < K) v.w = s[k + 3];
+          }
+          *reinterpret_cast<float4*>(d) = v;
+        }
+      }
+    }
+  };
+
+  const int nsteps = ceil_div(max(b_end - b_begin, 0), kWgRows);
+  if (nsteps > 0) {
+    stage(b_begin, 0);
+    cp_async_commit();
+  }
+  for (int s = 0; s < nsteps; ++s) {
+    if (s + 1 < nsteps) {
+      stage(b_begin + (s + 1) * kWgRows, (s + 1) & 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int buf = s & 1;
+#pragma unroll 8
+    for (int r = 0; r < kWgRows; ++r) {
+      const float4 z = *reinterpret_cast<const float4*>(&zs[buf][r][4 * in_]);
+      const float4 x = *reinterpret_cast<const float4*>(&as[buf][r][4 * ik]);
+      acc[0][0] = fmaf(z.x, x.x, acc[0][0]); acc[0][1] = fmaf(z.x, x.y, acc[0][1]);
+      acc[0][2] = fmaf(z.x, x.z, acc[0][2]); acc[0][3] = fmaf(z.x, x.w, acc[0][3]);
+      acc[1][0] = fmaf(z.y, x.x, acc[1][0]); acc[1][1] = fmaf(z.y, x.y, acc[1][1]);
+      acc[1][2] = fmaf(z.y, x.z, acc[1][2]); acc[1][3] = fmaf(z.y, x.w, acc[1][3]);
+      acc[2][0] = fmaf(z.z, x.x, acc[2][0]); acc[2][1] = fmaf(z.z, x.y, acc[2][1]);
+      acc[2][2] = fmaf(z.z, x.z, acc[2][2]); acc[2][3] = fmaf(z.z, x.w, acc[2][3]);
+      acc[3][0] = fmaf(z.w, x.x, acc[3][0]); acc[3][1] = fmaf(z.w, x.y, acc[3][1]);
+      acc[3][2] = fmaf(z.w, x.z, acc[3][2]); acc[3][3] = fmaf(z.w, x.w, acc[3][3]);
+      bsum[0] += z.x; bsum[1] += z.y; bsum[2] += z.z; bsum[3] += z.w;
+    }
+    __syncthreads();
+  }
+
+  float* g = p.gpart + (size_t)split * p.P;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + 4 * in_ + i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + 4 * ik + j;
+      if (k < K) g[Ly.w_off + (size_t)n * K + k] = acc[i][j];
+    }
+    if (tk == 0 && ik == 0) g[Ly.b_off + n] = bsum[i];
+  }
+}
+
+// g[i] = sum_s gpart[s*P + i]
+__global__ void grad_reduce_kernel(const float* __restrict__ gpart, int splits, long long n,
+                                   float* __restrict__ g) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float s = gpart[i];
+    for (int k = 1; k < splits; ++k) s += gpart[(size_t)k * n + i];
+    g[i] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Fused Adam (+ Polyak).  Mirrors torch.optim.Adam's single-tensor path
+// (non-amsgrad, non-capturable):
+//   g   = sum_s grad[s] * grad_scale (+ wd * p)
+//   m   = lerp(m, g, 1-b1);  v = v*b2 + (1-b2)*g*g
+//   bc1 = 1 - b1^t, bc2 = 1 - b2^t (double), step_size = lr/bc1
+//   p  -= step_size * m / (sqrt(v)/sqrt(bc2) + eps)
+// then target = tau*p + (1-tau)*target  (SoftUpdate.step on the updated source).
+// ---------------------------------------------------------------------------
+struct AdamDev {
+  rb200_adam_args_t a;
+};
+
+__global__ void __launch_bounds__(256) adam_soft_kernel(const AdamDev d) {
+  const rb200_adam_args_t& a = d.a;
+  const long long t = *a.step + 1;
+  const double bc1 = 1.0 - pow(a.beta1, (double)t);
+  const double bc2 = 1.0 - pow(a.beta2, (double)t);
+  const float step_size = (float)(a.lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  const float eps = (float)a.eps;
+  const float w1 = (float)(1.0 - a.beta1);
+  const float b2 = (float)a.beta2;
+  const float w2 = (float)(1.0 - a.beta2);
+  const float wd = (float)a.weight_decay;
+  const long long n = a.n;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float g = a.grad[i];
+    for (int s = 1; s < a.splits; ++s) g += a.grad[(size_t)s * n + i];
+    g *= a.grad_scale;
+    float p = a.params[i];
+    if (wd != 0.f) g = fmaf(wd, p, g);
+    float m = a.exp_avg[i];
+    float v = a.exp_avg_sq[i];
+    // rounding mirrors ATen's CPU kernels: lerp = fma(w, g-m, m); addcmul / addcdiv
+    // evaluate value*t1 first, each product/quotient rounded separately.
+    m = fmaf(w1, __fsub_rn(g, m), m);
+    v = __fadd_rn(__fmul_rn(v, b2), __fmul_rn(__fmul_rn(w2, g), g));
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), eps);
+    p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-step_size, m), denom));
+    a.params[i] = p;
+    a.exp_avg[i] = m;
+    a.exp_avg_sq[i] = v;
+    if (a.target) {
+      const float tg = a.target[i];
+      a.target[i] = __fadd_rn(__fmul_rn(a.tau, p), __fmul_rn(a.one_minus_tau, tg));
+    }
+  }
+  // last block to finish bumps the step counter (every block has read it by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned done = atomicAdd(a.block_counter, 1u);
+    if (done == gridDim.x - 1) {
+      *a.step = t;
+      *a.block_counter = 0u;
+    }
+  }
+}
+
+__global__ void soft_update_kernel(float* __restrict__ target, const float* __restrict__ src,
+                                   long long n, float tau, float omt) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    target[i] = __fadd_rn(__fmul_rn(tau, src[i]), __fmul_rn(omt, target[i]));
+}
+
+}  // namespace rb200
+
+using namespace rb200;
+
+extern "C" int rb200_wgrad_splits(int batch) {
+  // enough batch splits that even a single 64x64 tile layer fills a good part of the
+  // 148 SMs; rows per split stay a multiple of the 32-row staging step.
+  int s = batch / 256;
+  if (s < 1) s = 1;
+  if (s > 32) s = 32;
+  return s;
+}
+
+extern "C" int rb200_mlp_wgrad(const rb200_mlp_t* net, const float* net_input, int32_t batch,
+                               const rb200_net_ws_t* ws, float* gpart, int32_t splits,
+                               void* stream) {
+  if (!net || !ws || !gpart) { set_last_error("rb200_mlp_wgrad: null argument"); return RB200_E_INVALID; }
+  if (int rc = validate_mlp(net, "net")) return rc;
+  if (batch <= 0 || splits <= 0) { set_last_error("rb200_mlp_wgrad: bad batch/splits"); return RB200_E_INVALID; }
+  WgradParams p = {};
+  p.n_layers = net->n_layers;
+  p.B = batch;
+  p.splits = splits;
+  p.rows_per_split = ceil_div(ceil_div(batch, splits), kWgRows) * kWgRows;
+  p.gpart = gpart;
+  p.P = net->n_params;
+  int tiles = 0;
+  for (int l = 0; l < net->n_layers; ++l) {
+    WgradLayer& L = p.L[l];
+    L.A = (l == 0) ? (net_input ? net_input : ws->input) : ws->hidden[l - 1];
+    L.dZ = ws->dz[l];
+    if (!L.A || !L.dZ) { set_last_error("rb200_mlp_wgrad: missing activation / dz for layer %d", l); return RB200_E_INVALID; }
+    L.K = net->dims[l];
+    L.N = net->dims[l + 1];
+    L.w_off = net->w_off[l];
+    L.b_off = net->b_off[l];
+    L.tiles_n = ceil_div(L.N, kWgTile);
+    L.tiles_k = ceil_div(L.K, kWgTile);
+    L.tile_start = tiles;
+    tiles += L.tiles_n * L.tiles_k;
+  }
+  for (int l = net->n_layers; l < kMaxLayers; ++l) p.L[l].tile_start = 1 << 30;
+  dim3 grid(tiles, splits);
+  wgrad_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(p);
+  return check_cuda(cudaGetLastError(), "wgrad_kernel launch");
+}
+
+extern "C" int rb200_grad_reduce(const float* gpart, int32_t splits, int64_t n, float* g,
+                                 void* stream) {
+  if (!gpart || !g || n <= 0 || splits <= 0) { set_last_error("rb200_grad_reduce: bad argument"); return RB200_E_INVALID; }
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  grad_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(gpart, splits, (long long)n, g);
+  return check_cuda(cudaGetLastError(), "grad_reduce_kernel launch");
+}
+
+extern "C" int rb200_adam_soft_update(const rb200_adam_args_t* a, void* stream) {
+  if (!a || !a->params || !a->grad || !a->exp_avg || !a->exp_avg_sq || !a->step || !a->block_counter) {
+    set_last_error("rb200_adam_soft_update: null argument"); return RB200_E_INVALID;
+  }
+  if (a->n <= 0 || a->splits <= 0) { set_last_error("rb200_adam_soft_update: bad n/splits"); return RB200_E_INVALID; }
+  AdamDev d;
+  d.a = *a;
+  int blocks = (int)((a->n + 255) / 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  adam_soft_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d);
+  return check_cuda(cudaGetLastError(), "adam_soft_kernel launch");
+}
+
+extern "C" int rb200_soft_update(float* target, const float* source, int64_t n, float tau,
+                                 float one_minus_tau, void* stream) {
+  if (!target || !source || n <= 0) { set_last_error("rb200_soft_update: bad argument"); return RB200_E_INVALID; }
+  if (target == source) return RB200_OK;  // aliased: soft_update.py:64-67 skips
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  soft_update_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(target, source, (long long)n, tau, one_minus_tau);
+  return check_cuda(cudaGetLastError(), "soft_update_kernel launch");
+}

@@ -1,0 +1,3 @@
+from .dqn_trainer import BCQConfig, DQNTrainer  # noqa: F401
+from .loop import run_update  # noqa: F401
+from .reagent_lightning_module import ReAgentLightningModule  # noqa: F401

@@ -1,0 +1,214 @@
+"""DQNTrainer with the reference's constructor, optimizer list and generator protocol
+(reagent/training/dqn_trainer.py:27-304), computed by three CUDA launches:
+
+  rb200_dqn_td_step   (K2+K2') TD target, loss, dZ chain        dqn_trainer.py:157-239
+  rb200_mlp_wgrad     weight gradients (split-K partials)        autograd Linear backward
+  rb200_adam_soft_update (K3)  Adam + Polyak                     optimizer.py:64-85, soft_update.py:47-71
+"""
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from .. import _lib
+from ..core import types as rlt
+from ..core.parameters import EvaluationParameters, RLParameters
+from ..optimizer import Optimizer__Union, SoftUpdate
+from .dqn_trainer_base import DQNTrainerBaseLightning
+from .workspace import NetWorkspace, param_grads, wgrad
+
+
+@dataclass(frozen=True)
+class BCQConfig:
+    drop_threshold: float = 0.1
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class DQNTrainer(DQNTrainerBaseLightning):
+    def __init__(
+        self,
+        q_network,
+        q_network_target,
+        reward_network=None,
+        q_network_cpe=None,
+        q_network_cpe_target=None,
+        metrics_to_score=None,
+        evaluation: Optional[EvaluationParameters] = None,
+        imitator=None,
+        actions: Optional[List[str]] = None,
+        rl: Optional[RLParameters] = None,
+        double_q_learning: bool = True,
+        bcq: Optional[BCQConfig] = None,
+        minibatch_size: int = 1024,
+        minibatches_per_step: int = 1,
+        optimizer: Optional[Optimizer__Union] = None,
+    ) -> None:
+        # @resolve_defaults in the reference (dqn_trainer.py:50): default_factory fields
+        evaluation = EvaluationParameters() if evaluation is None else evaluation
+        actions = [] if actions is None else actions
+        rl = RLParameters() if rl is None else rl
+        optimizer = Optimizer__Union.default() if optimizer is None else optimizer
+        super().__init__(rl, metrics_to_score=metrics_to_score, actions=actions,
+                         evaluation_parameters=evaluation)
+        assert self._actions is not None, "Discrete-action DQN needs action names"
+        self.double_q_learning = double_q_learning
+        self.minibatch_size = minibatch_size
+        self.minibatches_per_step = minibatches_per_step or 1
+        self.q_network = q_network
+        self.q_network_target = q_network_target
+        self.q_network_optimizer = optimizer
+        self._initialize_cpe(reward_network, q_network_cpe, q_network_cpe_target,
+                             optimizer=optimizer)
+        self.bcq = bcq is not None
+        if self.bcq:
+            raise NotImplementedError("batch-constrained q-learning is out of scope of the fused path")
+        self._ws = None
+        self.all_action_scores = None
+
+    # ------------------------------------------------------------------
+    def configure_optimizers(self):
+        """[Adam(q_network), SoftUpdate(target <- q_network)] (dqn_trainer.py:119-155)."""
+        optimizers = []
+        target_params = list(self.q_network_target.parameters())
+        source_params = list(self.q_network.parameters())
+        optimizers.append(
+            self.q_network_optimizer.make_optimizer_scheduler(self.q_network.parameters()))
+        optimizers.append(
+            SoftUpdate.make_optimizer_scheduler(target_params, source_params, tau=self.tau))
+        return optimizers
+
+    # ------------------------------------------------------------------
+    def _workspace(self, B: int, device):
+        ws = self._ws
+        if ws is None or ws["B"] != B or ws["dev"] != device:
+            arena = self.q_network.arena
+            ntiles = (B + 15) // 16
+            ws = {
+                "B": B, "dev": device,
+                "net": NetWorkspace(arena, B, device),
+                "scores": torch.empty(B, self.num_actions, device=device),
+                "td_target": torch.empty(B, device=device),
+                "q_sel": torch.empty(B, device=device),
+                "next_idx": torch.empty(B, dtype=torch.int32, device=device),
+                "loss_partials": torch.zeros(ntiles, device=device),
+                "loss": torch.zeros(1, device=device),
+                "counter": torch.zeros(1, dtype=torch.int32, device=device),
+            }
+            self._ws = ws
+        return ws
+
+    def _td_step(self, batch: rlt.DiscreteDqnInput, do_backward: bool = True) -> torch.Tensor:
+        """Fused TD target + loss (+ backward).  Returns the device loss scalar (shape [])."""
+        state = _f32c(batch.state.float_features)
+        if not state.is_cuda:
+            raise _lib.Rb200Error(
+                "DQNTrainer: training batch must be on the GPU (reagent_b200 has no CPU path)")
+        B = state.shape[0]
+        ws = self._workspace(B, state.device)
+        a = _lib.DqnArgsT()
+        keep = []
+
+        def P(t):
+            t = _f32c(t)
+            keep.append(t)
+            return _lib.ptr(t)
+
+        a.batch = B
+        a.state = P(state)
+        a.next_state = P(batch.next_state.float_features)
+        a.action = P(batch.action)
+        a.next_action = P(batch.next_action)
+        a.reward = P(batch.reward.reshape(-1))
+        a.not_terminal = P(batch.not_terminal.reshape(-1))
+        a.possible_next_actions_mask = P(batch.possible_next_actions_mask)
+        a.discount_src = None
+        a.discount_mode = _lib.DISCOUNT_CONST
+        if self.use_seq_num_diff_as_time_diff:
+            assert self.multi_steps is None
+            a.discount_src = P(batch.time_diff.reshape(-1))
+            a.discount_mode = _lib.DISCOUNT_POW
+        if self.multi_steps is not None:
+            assert batch.step is not None
+            a.discount_src = P(batch.step.reshape(-1))
+            a.discount_mode = _lib.DISCOUNT_POW
+        a.reward_boost = P(self.reward_boosts.reshape(-1)) if self._has_reward_boost else None
+        a.gamma = float(self.gamma)
+        a.double_q = int(bool(self.double_q_learning))
+        a.maxq = int(bool(self.maxq_learning))
+        a.loss_kind = self.q_network_loss_kind
+        a.do_backward = int(do_backward)
+        a.all_action_scores = ws["scores"].data_ptr()
+        a.td_target = ws["td_target"].data_ptr()
+        a.q_selected = ws["q_sel"].data_ptr()
+        a.next_action_idx = ws["next_idx"].data_ptr()
+        a.loss_partials = ws["loss_partials"].data_ptr()
+        a.loss = ws["loss"].data_ptr()
+        a.tile_counter = ws["counter"].data_ptr()
+        qd, qtd = self.q_network.arena.desc(), self.q_network_target.arena.desc()
+        rc = _lib.lib().rb200_dqn_td_step(qd, qtd, a, ws["net"].c, _lib.cur_stream())
+        _lib.check(rc, "rb200_dqn_td_step")
+        if do_backward:
+            wgrad(self.q_network.arena, ws["net"], state, B)
+        self.all_action_scores = ws["scores"]
+        return ws["loss"].reshape(())
+
+    # ------------------------------------------------------------------
+    def train_step_gen(self, training_batch: rlt.DiscreteDqnInput, batch_idx: int):
+        """Yields (td_loss, soft_update_loss) -- dqn_trainer.py:241-304 with CPE off."""
+        self._check_input(training_batch)
+        td_loss = self._td_step(training_batch)
+        yield self.fused_loss(td_loss)
+        td_loss = td_loss.detach()
+        if self.has_real_reporter or self.logger:
+            self._log_dqn(td_loss, training_batch)
+        yield self.soft_update_result()
+
+    def train_batch(self, training_batch: rlt.DiscreteDqnInput, batch_idx: int = 0):
+        """Fast path: one full update in 3 launches, Polyak fused into the Adam kernel.
+        Same arithmetic as driving train_step_gen with reagent_b200.training.loop."""
+        opts = self.optimizers()
+        self._td_step(training_batch)
+        opts[0].fused_step(target=self.q_network_target.arena, tau=self.tau)
+        self.all_batches_processed += 1
+        return self._ws["loss"]
+
+    @torch.no_grad()
+    def compute_td_loss_only(self, batch: rlt.DiscreteDqnInput) -> torch.Tensor:
+        """validation_step's eval_td_loss (dqn_trainer.py:363-379): forward/loss, no grads."""
+        return self._td_step(batch, do_backward=False).clone()
+
+    def q_network_grads(self):
+        """Per-parameter gradients of the last fused backward (inspection / tests)."""
+        return param_grads(self.q_network.arena, list(self.q_network.parameters()))
+
+    # ------------------------------------------------------------------
+    def _log_dqn(self, td_loss, training_batch):
+        """dqn_trainer.py:292-347 -- only evaluated when a reporter/logger is attached."""
+        scores = self.all_action_scores
+        logged_action_idxs = torch.argmax(training_batch.action, dim=1, keepdim=True)
+        rewards = self.boost_rewards(training_batch.reward, training_batch.action)
+        mask = (training_batch.possible_actions_mask if self.maxq_learning
+                else training_batch.action)
+        model_action_idxs = self.get_max_q_values(scores, mask.float())[1]
+        extras = training_batch.extras
+        self.reporter.log(
+            td_loss=td_loss,
+            logged_actions=logged_action_idxs,
+            logged_propensities=None if extras is None else extras.action_probability,
+            logged_rewards=rewards,
+            logged_values=None,
+            model_values=scores,
+            model_values_on_logged_actions=None,
+            model_action_idxs=model_action_idxs,
+        )
+        if self.logger:
+            self.logger.log_metrics(
+                {"td_loss": td_loss, "logged_rewards": rewards.mean()},
+                step=self.all_batches_processed)

@@ -1,0 +1,47 @@
+"""Pins the CPU restatement (oracle/td_oracle.py) against golden vectors produced by the
+UNMODIFIED reference (oracle/make_golden.py).  CPU only."""
+import pytest
+import torch
+
+from oracle import td_oracle as O
+from tests import golden_util as G
+
+DQN_CASES = ["dqn_huber_double", "dqn_mse_single_masked", "dqn_sarsa", "dqn_multistep_boost",
+             "dqn_timediff_odd_dims"]
+
+
+def _dqn_kwargs(meta, batch):
+    kw = dict(double_q=meta["double_q"], maxq=meta["maxq"], loss=meta["loss"])
+    if meta["multi_steps"] is not None:
+        kw["discount_src"] = batch["step"]
+    elif meta["time_diff"]:
+        kw["discount_src"] = batch["time_diff"]
+    if meta["boost"]:
+        rb = torch.zeros(1, meta["A"])
+        for k, v in meta["boost"].items():
+            rb[0, int(k)] = v
+        kw["reward_boost"] = rb
+    return kw
+
+
+@pytest.mark.parametrize("name", DQN_CASES)
+def test_dqn_oracle_matches_reference(name):
+    arrays, meta = G.load(name)
+    acts = meta["acts"] + ["linear"]
+    q = G.oracle_net(arrays, "q0", acts, requires_grad=True)
+    qt = G.oracle_net(arrays, "qt0", acts)
+    batch = G.batch_tensors(arrays)
+    adam = O.AdamState(O.net_params(q), lr=meta["lr"])
+    kw = _dqn_kwargs(meta, batch)
+    for it in range(meta["n_updates"]):
+        loss, grads, aux = O.dqn_update(q, qt, adam, batch, gamma=meta["gamma"], tau=meta["tau"], **kw)
+        assert abs(loss - arrays["losses"][it]) <= 1e-6 * max(1.0, abs(arrays["losses"][it]))
+        if it == 0:
+            for i, g in enumerate(grads):
+                assert G.rel_err(g, arrays[f"grad0.{i}"]) < 1e-6
+            assert G.rel_err(aux["all_q"], arrays["all_q0"]) < 1e-6
+    for i in range(len(q["W"])):
+        assert G.rel_err(q["W"][i], arrays[f"qN.W{i}"]) < 1e-6
+        assert G.rel_err(q["b"][i], arrays[f"qN.b{i}"]) < 1e-6
+        assert G.rel_err(qt["W"][i], arrays[f"qtN.W{i}"]) < 1e-6
+        assert G.rel_err(qt["b"][i], arrays[f"qtN.b{i}"]) < 1e-6
