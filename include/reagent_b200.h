@@ -66,10 +66,42 @@ typedef struct rb200_net_ws {
   float* input;
 } rb200_net_ws_t;
 
+/* feature types: reagent/preprocessing/identify_types.py:9-30 (FEATURE_TYPES order) */
+#define RB200_FT_BINARY 0
+#define RB200_FT_PROBABILITY 1
+#define RB200_FT_CONTINUOUS 2
+#define RB200_FT_BOXCOX 3
+#define RB200_FT_ENUM 4
+#define RB200_FT_QUANTILE 5
+#define RB200_FT_CONTINUOUS_ACTION 6
+#define RB200_FT_DISCRETE_ACTION 7
+#define RB200_FT_DO_NOT_PREPROCESS 8
+#define RB200_FT_CLIP_LOG 9
+
+/* One OUTPUT column of the dense preprocessor (reagent/preprocessing/preprocessor.py):
+ * out[:, j] = transform_type(in[:, src_col]; p0..p3 [, quantiles q_off..q_off+q_cnt)).
+ *   PROBABILITY: p0=1e-5 p1=1-1e-5 (as f32)     CONTINUOUS: p0=mean p1=stddev
+ *   BOXCOX: p0=mean p1=stddev p2=shift p3=lambda ENUM: p0=possible value of this column
+ *   QUANTILE: p0=len(quantiles)-1 p1=max p2=min, q_* = padded boundaries
+ *   CONTINUOUS_ACTION: p0=min_serving p1=scaling_factor p2=min_training p3=-1+EPS */
+typedef struct rb200_feature_col {
+  int32_t src_col;
+  int32_t type;
+  float p0, p1, p2, p3;
+  int32_t q_off, q_cnt;
+} rb200_feature_col_t;
+
 const char* rb200_last_error(void);
 int rb200_version(void);
 /* number of SMs / max opt-in smem of the current device (host query helpers) */
 int rb200_device_info(int* sm_count, int* max_smem_optin);
+
+/* P1: Preprocessor.forward(input, input_presence_byte) -- reagent/preprocessing/
+ * preprocessor.py:115-170.  `cols` / `quantiles` are device arrays; presence may be NULL
+ * (all present), uint8/bool [rows,f_in] or float [rows,f_in]. */
+int rb200_preprocess(const float* input, const void* presence, int32_t presence_is_float,
+                     int64_t rows, int32_t f_in, int32_t f_out, const rb200_feature_col_t* cols,
+                     const float* quantiles, float* out, void* stream);
 
 /* Fused whole-MLP forward out = net(cat(in0, in1)) over row tiles; in1 may be NULL.
  * Replaces FullyConnectedNetwork.forward (reagent/models/fully_connected_network.py:157-163)
@@ -154,6 +186,107 @@ int rb200_adam_soft_update(const rb200_adam_args_t* a, void* stream);
 /* stand-alone Polyak update (SoftUpdate.step when not fused) */
 int rb200_soft_update(float* target, const float* source, int64_t n, float tau,
                       float one_minus_tau, void* stream);
+
+
+/* ------------------------------------------------------------------------- */
+/* K1: fused replay sampling over device-resident storage.                     */
+/* Replaces SumTree.stratified_sample/sample (reagent/replay_memory/sum_tree.py:93-153),*/
+/* ReplayBuffer.sample_index_batch / sample_transition_batch                   */
+/* (circular_replay_buffer.py:589-706, :741-774), PrioritizedReplayBuffer's    */
+/* sampling_probabilities (prioritized_replay_buffer.py:116-147), the dense    */
+/* Preprocessor on state/next_state (preprocessing/preprocessor.py:115-170) and*/
+/* the InputMakers (gym/preprocessors/trainer_preprocessor.py:72-227).         */
+/* Random numbers come from the HOST (bit-exact index parity): `query` are the */
+/* stratified uniforms of SumTree.stratified_sample, `ranks` torch.randint's   */
+/* draws; rare invalid-index retries are resolved on the host and passed as    */
+/* overrides (see reagent_b200/replay_memory/prioritized_replay_buffer.py).    */
+/* ------------------------------------------------------------------------- */
+#define RB200_SAMPLE_PRIORITIZED 0
+#define RB200_SAMPLE_UNIFORM 1
+#define RB200_SAMPLE_GIVEN 2
+#define RB200_VALID_BLOCK 256
+#define RB200_MAX_GATHER_SPECS 12
+
+typedef struct rb200_gather_spec {
+  const void* src;     /* [capacity, row_bytes] */
+  void* dst;           /* [batch, row_bytes]    */
+  int32_t row_bytes;
+  int32_t which;       /* 0: sampled index, 1: next index */
+} rb200_gather_spec_t;
+
+typedef struct rb200_sample_args {
+  int32_t batch, capacity, update_horizon, mode;
+  int32_t timeline_next;              /* next index = i+1 instead of i+steps */
+  /* index sources */
+  const double* tree;                 /* fp64 heap: level l at [2^l-1, 2^(l+1)-1) */
+  int32_t tree_depth;
+  const double* query;                /* [B] in [0,1) */
+  const int32_t* override_pos;        /* [n_override] batch positions */
+  const int64_t* override_idx;        /* [n_override] replacement indices */
+  int32_t n_override;
+  const int64_t* ranks;               /* [B] rank among valid slots */
+  const uint8_t* valid;               /* [capacity] */
+  const int32_t* valid_block_offsets; /* [n_valid_blocks+1] */
+  int32_t n_valid_blocks;
+  const int64_t* indices_in;          /* [B] */
+  /* storage */
+  const uint8_t* terminal;            /* [capacity] */
+  const float* reward;                /* [capacity] */
+  const float* decays;                /* [update_horizon] gamma**k as f32 */
+  const float* obs;                   /* [capacity, obs_dim] or NULL */
+  int32_t obs_dim, obs_out_dim;
+  const rb200_feature_col_t* cols;    /* NULL: raw copy */
+  const float* quantiles;
+  float* state;                       /* [B, obs_out_dim] */
+  float* next_state;
+  /* discrete action (int64 scalar per slot) */
+  const int64_t* action_i64;
+  int32_t num_actions;
+  int64_t* action_out_i64;            /* [B] */
+  int64_t* next_action_out_i64;       /* [B] */
+  float* action_onehot;               /* [B, num_actions] */
+  float* next_action_onehot;          /* zeroed on terminal rows */
+  /* continuous action (f32 row per slot) */
+  const float* action_f32;
+  int32_t action_dim;
+  float* action_out_raw;              /* [B, action_dim] */
+  float* next_action_out_raw;
+  float* action_rescaled;             /* [B, action_dim] rescaled to [train_low, train_high] */
+  float* next_action_rescaled;        /* zeroed on terminal rows */
+  const float* action_low;            /* [action_dim] */
+  const float* action_high;
+  float train_low, train_high;
+  /* scalar outputs, all [B] */
+  float* reward_out;
+  float* next_reward_out;
+  uint8_t* terminal_out;
+  float* not_terminal_out;
+  int64_t* indices_out;
+  int64_t* step_out;
+  float* step_f32_out;
+  float* sampling_prob_out;
+  int32_t n_specs;
+  rb200_gather_spec_t specs[RB200_MAX_GATHER_SPECS];
+} rb200_sample_args_t;
+
+int rb200_replay_sample(const rb200_sample_args_t* args, void* stream);
+/* validity bitmap -> per-256-slot counts and exclusive offsets (uniform sampling index);
+ * counts [ceil(cap/256)], offsets [ceil(cap/256)+1] */
+int rb200_valid_index_build(const uint8_t* valid, int64_t capacity, int32_t* counts,
+                            int32_t* offsets, void* stream);
+
+/* ---- host-side helpers (plain C, no CUDA; pointers are HOST memory) -------- */
+/* MT19937 with CPython's exact stream: fills out[i] = lo[i] + (hi[i]-lo[i])*random()
+ * (random.uniform, Lib/random.py) or random() itself when lo/hi are NULL.
+ * state624 + *index are CPython's random.getstate()[1] (624 words + position). */
+void rb200_mt19937_uniform_host(uint32_t* state624, int32_t* index, const double* lo_host,
+                                const double* hi_host, double* out_host, int64_t n);
+/* SumTree.set for a batch, sequentially, on a host fp64 heap (sum_tree.py:164-189).
+ * Returns -1 if a value is negative (nothing after it is applied). */
+int rb200_sumtree_set_host(double* tree_host, int32_t depth, const int64_t* idx_host,
+                           const double* val_host, int64_t n, double* max_recorded_host);
+/* SumTree.sample(query) on the host heap (sum_tree.py:93-131). */
+int64_t rb200_sumtree_sample_host(const double* tree_host, int32_t depth, double query);
 
 #ifdef __cplusplus
 }

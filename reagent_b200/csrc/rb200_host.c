@@ -1,0 +1,82 @@
+/* reagent_b200 -- host-side helpers of the replay path (plain C, no CUDA).
+ *
+ * MT19937: the generator behind Python's `random` (CPython Modules/_randommodule.c,
+ * algorithm of Matsumoto & Nishimura 2002), restated so that the stratified query values
+ * of SumTree.stratified_sample (reagent/replay_memory/sum_tree.py:149-153:
+ * random.uniform(lo, hi) = lo + (hi-lo)*random()) are reproduced bit for bit at C speed
+ * from the interpreter's own state (random.getstate() / setstate()).
+ */
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/reagent_b200.h"
+
+#define MT_N 624
+#define MT_M 397
+
+static uint32_t mt_next(uint32_t* mt, int32_t* index) {
+  static const uint32_t mag01[2] = {0x0U, 0x9908b0dfU};
+  uint32_t y;
+  if (*index >= MT_N) {
+    int kk;
+    for (kk = 0; kk < MT_N - MT_M; kk++) {
+      y = (mt[kk] & 0x80000000U) | (mt[kk + 1] & 0x7fffffffU);
+      mt[kk] = mt[kk + MT_M] ^ (y >> 1) ^ mag01[y & 0x1U];
+    }
+    for (; kk < MT_N - 1; kk++) {
+      y = (mt[kk] & 0x80000000U) | (mt[kk + 1] & 0x7fffffffU);
+      mt[kk] = mt[kk + (MT_M - MT_N)] ^ (y >> 1) ^ mag01[y & 0x1U];
+    }
+    y = (mt[MT_N - 1] & 0x80000000U) | (mt[0] & 0x7fffffffU);
+    mt[MT_N - 1] = mt[MT_M - 1] ^ (y >> 1) ^ mag01[y & 0x1U];
+    *index = 0;
+  }
+  y = mt[(*index)++];
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680U;
+  y ^= (y << 15) & 0xefc60000U;
+  y ^= (y >> 18);
+  return y;
+}
+
+void rb200_mt19937_uniform_host(uint32_t* state624, int32_t* index, const double* lo,
+                                const double* hi, double* out, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) {
+    /* random(): 53-bit resolution double in [0,1) */
+    const uint32_t a = mt_next(state624, index) >> 5, b = mt_next(state624, index) >> 6;
+    const double r = (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+    out[i] = (lo && hi) ? lo[i] + (hi[i] - lo[i]) * r : r;
+  }
+}
+
+int rb200_sumtree_set_host(double* tree, int32_t depth, const int64_t* idx, const double* val,
+                           int64_t n, double* max_recorded) {
+  for (int64_t i = 0; i < n; ++i) {
+    const double value = val[i];
+    if (value < 0.0) return -1;
+    if (max_recorded && value > *max_recorded) *max_recorded = value;
+    int64_t node = idx[i];
+    const double delta = value - tree[((int64_t)1 << depth) - 1 + node];
+    for (int32_t lvl = depth; lvl >= 0; --lvl) {
+      tree[((int64_t)1 << lvl) - 1 + node] += delta;
+      node /= 2;
+    }
+  }
+  return 0;
+}
+
+int64_t rb200_sumtree_sample_host(const double* tree, int32_t depth, double query) {
+  double q = query * tree[0];
+  int64_t node = 0;
+  for (int32_t lvl = 1; lvl <= depth; ++lvl) {
+    const int64_t left = node * 2;
+    const double left_sum = tree[((int64_t)1 << lvl) - 1 + left];
+    if (q < left_sum) {
+      node = left;
+    } else {
+      node = left + 1;
+      q -= left_sum;
+    }
+  }
+  return node;
+}
