@@ -285,6 +285,11 @@ void rb200_mt19937_uniform_host(uint32_t* state624, int32_t* index, const double
  * Returns -1 if a value is negative (nothing after it is applied). */
 int rb200_sumtree_set_host(double* tree_host, int32_t depth, const int64_t* idx_host,
                            const double* val_host, int64_t n, double* max_recorded_host);
+/* Validity bookkeeping of n consecutive ReplayBuffer.add() calls, stack_size == 1
+ * (circular_replay_buffer.py:468-522).  state = {add_count, episode length, num valid}. */
+void rb200_replay_add_batch_host(const uint8_t* terminal_in_host, int64_t n, int64_t capacity,
+                                 int32_t update_horizon, uint8_t* valid_host,
+                                 uint8_t* terminal_store_host, int64_t* state_host);
 /* SumTree.sample(query) on the host heap (sum_tree.py:93-131). */
 int64_t rb200_sumtree_sample_host(const double* tree_host, int32_t depth, double query);
 

@@ -125,6 +125,152 @@ def dqn_case(name, *, B=48, S=12, A=5, sizes=(24, 20), acts=("relu", "relu"), lo
     _save(name, arrays, meta)
 
 
+# ---------------------------------------------------------------------------
+# replay buffers: the add stream is recorded so the test can replay it
+# ---------------------------------------------------------------------------
+def _make_stream(n, S, A, seed, p_term, continuous=False, with_extra=False):
+    rng = np.random.RandomState(seed)
+    st = dict(
+        observation=rng.randn(n, S).astype(np.float32),
+        reward=rng.randn(n).astype(np.float32),
+        terminal=(rng.rand(n) < p_term),
+        priority=rng.uniform(0.1, 10.0, size=n),
+    )
+    if continuous:
+        st["action"] = rng.uniform(-0.99, 0.99, size=(n, A)).astype(np.float32)
+    else:
+        st["action"] = rng.randint(0, A, size=n).astype(np.int64)
+    if with_extra:
+        st["log_prob"] = rng.randn(n).astype(np.float32)
+        st["mask"] = (rng.rand(n, A) > 0.3).astype(np.float32)
+    return st
+
+
+def replay_case(name, *, prioritized, cap, n_add, B, horizon=1, stack=1, gamma=0.9, S=6, A=4,
+                seed=0, p_term=0.08, continuous=False, with_extra=False, n_samples=3,
+                zero_priority_every=0):
+    import random
+    crb = ref("reagent.replay_memory.circular_replay_buffer")
+    prb = ref("reagent.replay_memory.prioritized_replay_buffer")
+    st = _make_stream(n_add, S, A, seed, p_term, continuous, with_extra)
+    if zero_priority_every:
+        st["priority"][::zero_priority_every] = 0.0
+    if prioritized:
+        rb = prb.PrioritizedReplayBuffer(stack_size=stack, replay_capacity=cap, batch_size=B,
+                                         update_horizon=horizon, gamma=gamma)
+    else:
+        rb = crb.ReplayBuffer(stack_size=stack, replay_capacity=cap, batch_size=B,
+                              update_horizon=horizon, gamma=gamma)
+    keys = ["observation", "action", "reward", "terminal"]
+    if with_extra:
+        keys += ["log_prob", "mask"]
+    if prioritized:
+        keys += ["priority"]
+    for t in range(n_add):
+        kw = {}
+        for k in keys:
+            v = st[k][t]
+            if k == "terminal":
+                v = bool(v)
+            elif k == "priority":
+                v = float(v)
+            elif k == "action" and not continuous:
+                v = int(v)
+            elif np.ndim(v) == 0:
+                v = float(v)
+            kw[k] = v
+        rb.add(**kw)
+    arrays = {f"stream.{k}": st[k] for k in keys}
+    arrays["valid"] = _np(rb._is_index_valid)
+    random.seed(seed + 100)
+    torch.manual_seed(seed + 100)
+    np.random.seed(seed + 100)
+    fields = None
+    for s_i in range(n_samples):
+        batch = rb.sample_transition_batch(batch_size=B)
+        fields = batch._fields
+        for f in fields:
+            if f in ("priority", "next_priority"):
+                continue  # uninitialised memory in the reference
+            v = getattr(batch, f)
+            if isinstance(v, torch.Tensor):
+                arrays[f"sample{s_i}.{f}"] = _np(v)
+    # everything valid, by explicit indices (exercises the `indices=` path)
+    allb = rb.sample_all_valid_transitions()
+    for f in allb._fields:
+        if f in ("priority", "next_priority", "sampling_probabilities"):
+            continue
+        v = getattr(allb, f)
+        if isinstance(v, torch.Tensor):
+            arrays[f"all.{f}"] = _np(v)
+    if prioritized:
+        idx = np.arange(0, min(cap, 32), dtype=np.int32)
+        arrays["get_priority"] = rb.get_priority(idx)
+        newp = np.linspace(0.5, 3.0, len(idx))
+        rb.set_priority(idx, newp)
+        arrays["set_priority.values"] = newp
+        arrays["tree_root_after_set"] = np.array([rb.sum_tree._total_priority()])
+        batch = rb.sample_transition_batch(batch_size=B)
+        arrays["after_set.indices"] = _np(batch.indices)
+        arrays["after_set.sampling_probabilities"] = _np(batch.sampling_probabilities)
+    meta = dict(kind="replay", prioritized=prioritized, cap=cap, n_add=n_add, B=B,
+                horizon=horizon, stack=stack, gamma=gamma, S=S, A=A, seed=seed,
+                continuous=continuous, with_extra=with_extra, n_samples=n_samples,
+                keys=keys, fields=list(fields))
+    _save(name, arrays, meta)
+
+
+# ---------------------------------------------------------------------------
+# dense preprocessor
+# ---------------------------------------------------------------------------
+def preprocessor_case(name, seed=0, B=64):
+    params = ref("reagent.core.parameters")
+    pp = ref("reagent.preprocessing.preprocessor")
+    NP = params.NormalizationParameters
+    rng = np.random.RandomState(seed)
+    spec = {
+        11: dict(feature_type="BINARY"),
+        3: dict(feature_type="PROBABILITY"),
+        7: dict(feature_type="CONTINUOUS", mean=0.3, stddev=1.7),
+        1: dict(feature_type="CONTINUOUS", mean=-2.0, stddev=0.4),
+        5: dict(feature_type="BOXCOX", boxcox_lambda=0.4, boxcox_shift=1.5, mean=0.2, stddev=1.3),
+        9: dict(feature_type="ENUM", possible_values=[2, 5, 9]),
+        4: dict(feature_type="ENUM", possible_values=[0, 1]),
+        8: dict(feature_type="QUANTILE", quantiles=[0.0, 10.0, 80.0, 100.0]),
+        2: dict(feature_type="QUANTILE", quantiles=[-1.0, 1.0]),
+        6: dict(feature_type="CONTINUOUS_ACTION", min_value=-2.0, max_value=3.0),
+        10: dict(feature_type="DISCRETE_ACTION"),
+        12: dict(feature_type="DO_NOT_PREPROCESS"),
+        13: dict(feature_type="CLIP_LOG"),
+    }
+    norm = {k: NP(**v) for k, v in spec.items()}
+    p = pp.Preprocessor(norm, device=torch.device("cpu"))
+    p.eval()
+    cols = {}
+    cols[11] = rng.randint(0, 2, B).astype(np.float32)
+    cols[3] = rng.uniform(0, 1, B)
+    cols[3][:3] = [0.0, 1.0, 0.5]
+    cols[7] = rng.randn(B) * 5
+    cols[1] = rng.randn(B) * 30   # exercises the +-11.513 clamp
+    cols[5] = rng.uniform(-1.4, 8, B)
+    cols[9] = rng.choice([2, 5, 9, 4], B)
+    cols[4] = rng.choice([0, 1], B)
+    cols[8] = rng.uniform(-20, 130, B)
+    cols[8][:4] = [0.0, 100.0, 10.0, 80.0]
+    cols[2] = rng.uniform(-2, 2, B)
+    cols[6] = rng.uniform(-2.5, 3.5, B)
+    cols[10] = rng.randint(0, 5, B)
+    cols[12] = rng.randn(B) * 100
+    cols[13] = rng.uniform(-1, 50, B)
+    x = np.stack([np.asarray(cols[f], dtype=np.float32) for f in p.sorted_features], axis=1)
+    presence = (rng.rand(*x.shape) > 0.15).astype(np.uint8)
+    out = p(torch.from_numpy(x), torch.from_numpy(presence))
+    out_all = p(torch.from_numpy(x), torch.ones_like(torch.from_numpy(presence)))
+    arrays = dict(x=x, presence=presence, out=_np(out), out_all_present=_np(out_all),
+                  sorted_features=np.array(p.sorted_features))
+    _save(name, arrays, dict(kind="preprocessor", spec={str(k): v for k, v in spec.items()}, B=B))
+
+
 def main():
     dqn_case("dqn_huber_double")
     dqn_case("dqn_mse_single_masked", loss="mse", double_q=False, random_masks=True, seed=1)
@@ -132,6 +278,19 @@ def main():
     dqn_case("dqn_multistep_boost", multi_steps=3, boost={"1": 0.5, "3": -0.25}, seed=3,
              acts=("leaky_relu", "tanh"))
     dqn_case("dqn_timediff_odd_dims", time_diff=True, B=37, S=7, A=3, sizes=(10, 6), seed=4)
+    replay_case("replay_uniform_h1", prioritized=False, cap=100, n_add=73, B=16)
+    replay_case("replay_uniform_h3_wrap", prioritized=False, cap=64, n_add=150, B=32, horizon=3,
+                seed=1, with_extra=True)
+    replay_case("replay_uniform_h5_cont", prioritized=False, cap=128, n_add=300, B=24, horizon=5,
+                seed=2, continuous=True, gamma=0.97)
+    replay_case("replay_uniform_stack3", prioritized=False, cap=96, n_add=200, B=16, horizon=2,
+                stack=3, seed=3)
+    replay_case("replay_per_h1", prioritized=True, cap=100, n_add=90, B=32, seed=4)
+    replay_case("replay_per_h3_wrap_zero", prioritized=True, cap=64, n_add=200, B=48, horizon=3,
+                seed=5, zero_priority_every=7, p_term=0.02)
+    replay_case("replay_per_big", prioritized=True, cap=4096, n_add=6000, B=256, horizon=1,
+                seed=6, S=8, n_samples=2)
+    preprocessor_case("preprocessor_all_types")
 
 
 if __name__ == "__main__":

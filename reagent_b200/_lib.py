@@ -87,6 +87,46 @@ class AdamArgsT(C.Structure):
     ]
 
 
+class FeatureColT(C.Structure):
+    _fields_ = [("src_col", C.c_int32), ("type", C.c_int32), ("p0", C.c_float), ("p1", C.c_float),
+                ("p2", C.c_float), ("p3", C.c_float), ("q_off", C.c_int32), ("q_cnt", C.c_int32)]
+
+
+MAX_GATHER_SPECS = 12
+VALID_BLOCK = 256
+SAMPLE_PRIORITIZED, SAMPLE_UNIFORM, SAMPLE_GIVEN = 0, 1, 2
+
+
+class GatherSpecT(C.Structure):
+    _fields_ = [("src", _vp), ("dst", _vp), ("row_bytes", C.c_int32), ("which", C.c_int32)]
+
+
+class SampleArgsT(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("capacity", C.c_int32), ("update_horizon", C.c_int32),
+        ("mode", C.c_int32), ("timeline_next", C.c_int32),
+        ("tree", _vp), ("tree_depth", C.c_int32), ("query", _vp),
+        ("override_pos", _vp), ("override_idx", _vp), ("n_override", C.c_int32),
+        ("ranks", _vp), ("valid", _vp), ("valid_block_offsets", _vp),
+        ("n_valid_blocks", C.c_int32), ("indices_in", _vp),
+        ("terminal", _vp), ("reward", _vp), ("decays", _vp),
+        ("obs", _vp), ("obs_dim", C.c_int32), ("obs_out_dim", C.c_int32),
+        ("cols", _vp), ("quantiles", _vp), ("state", _vp), ("next_state", _vp),
+        ("action_i64", _vp), ("num_actions", C.c_int32),
+        ("action_out_i64", _vp), ("next_action_out_i64", _vp),
+        ("action_onehot", _vp), ("next_action_onehot", _vp),
+        ("action_f32", _vp), ("action_dim", C.c_int32),
+        ("action_out_raw", _vp), ("next_action_out_raw", _vp),
+        ("action_rescaled", _vp), ("next_action_rescaled", _vp),
+        ("action_low", _vp), ("action_high", _vp),
+        ("train_low", C.c_float), ("train_high", C.c_float),
+        ("reward_out", _vp), ("next_reward_out", _vp), ("terminal_out", _vp),
+        ("not_terminal_out", _vp), ("indices_out", _vp), ("step_out", _vp),
+        ("step_f32_out", _vp), ("sampling_prob_out", _vp),
+        ("n_specs", C.c_int32), ("specs", GatherSpecT * MAX_GATHER_SPECS),
+    ]
+
+
 class Rb200Error(RuntimeError):
     pass
 
@@ -104,6 +144,17 @@ def _declare(lib):
                                       C.POINTER(NetWsT), _vp]
     lib.rb200_mlp_forward.argtypes = [C.POINTER(MlpT), _vp, C.c_int32, _vp, C.c_int32, C.c_int32,
                                       _vp, _vp]
+    lib.rb200_preprocess.argtypes = [_vp, _vp, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _vp,
+                                     _vp, _vp, _vp]
+    lib.rb200_replay_sample.argtypes = [C.POINTER(SampleArgsT), _vp]
+    lib.rb200_valid_index_build.argtypes = [_vp, C.c_int64, _vp, _vp, _vp]
+    lib.rb200_mt19937_uniform_host.argtypes = [_vp, C.POINTER(C.c_int32), _vp, _vp, _vp, C.c_int64]
+    lib.rb200_mt19937_uniform_host.restype = None
+    lib.rb200_sumtree_set_host.argtypes = [_vp, C.c_int32, _vp, _vp, C.c_int64, _vp]
+    lib.rb200_sumtree_sample_host.argtypes = [_vp, C.c_int32, C.c_double]
+    lib.rb200_sumtree_sample_host.restype = C.c_int64
+    lib.rb200_replay_add_batch_host.argtypes = [_vp, C.c_int64, C.c_int64, C.c_int32, _vp, _vp, _vp]
+    lib.rb200_replay_add_batch_host.restype = None
     lib.rb200_wgrad_splits.argtypes = [C.c_int]
     lib.rb200_mlp_wgrad.argtypes = [C.POINTER(MlpT), _vp, C.c_int32, C.POINTER(NetWsT), _vp,
                                     C.c_int32, _vp]

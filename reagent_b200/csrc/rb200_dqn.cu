@@ -146,9 +146,13 @@ dqn_td_rows_kernel(const Mlp q, const Mlp qt, const DqnDev p) {
 #define RB200_LAUNCH_DQN(TM_, KC_, grid, smem, stream, ...)                                   \
   do {                                                                                        \
     auto kfn = dqn_td_rows_kernel<TM_, KC_>;                                                  \
-    cudaError_t e_ = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                          (int)(smem));                                       \
-    if (e_ != cudaSuccess) return check_cuda(e_, "cudaFuncSetAttribute(dqn)");                \
+    static size_t configured_ = 0; /* set once (not inside CUDA-graph capture) */            \
+    if (configured_ < (size_t)(smem)) {                                                       \
+      cudaError_t e_ = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            (int)(smem));                                     \
+      if (e_ != cudaSuccess) return check_cuda(e_, "cudaFuncSetAttribute(dqn)");               \
+      configured_ = (size_t)(smem);                                                           \
+    }                                                                                         \
     kfn<<<grid, kThreads, smem, stream>>>(__VA_ARGS__);                                       \
   } while (0)
 

@@ -80,3 +80,33 @@ int64_t rb200_sumtree_sample_host(const double* tree, int32_t depth, double quer
   }
   return node;
 }
+
+/* Validity bookkeeping of N consecutive ReplayBuffer.add() calls with stack_size == 1
+ * (reagent/replay_memory/circular_replay_buffer.py:468-522), applied to host arrays.
+ * state[0]=add_count, state[1]=transitions in current episode, state[2]=num valid. */
+void rb200_replay_add_batch_host(const uint8_t* terminal_in, int64_t n, int64_t capacity,
+                                 int32_t update_horizon, uint8_t* valid, uint8_t* terminal_store,
+                                 int64_t* state) {
+  int64_t add_count = state[0], ep = state[1], nvalid = state[2];
+  for (int64_t t = 0; t < n; ++t) {
+    const int64_t cur = add_count % capacity;
+    const int64_t last = (cur - 1 + capacity) % capacity;
+    if (add_count == 0 || terminal_store[last]) ep = 0;
+    if (valid[cur]) { valid[cur] = 0; --nvalid; }
+    if (ep >= update_horizon) {
+      const int64_t i = ((cur - update_horizon) % capacity + capacity) % capacity;
+      if (!valid[i]) { valid[i] = 1; ++nvalid; }
+    }
+    terminal_store[cur] = terminal_in[t] ? 1 : 0;
+    ++add_count;
+    ++ep;
+    if (terminal_in[t]) {
+      const int64_t back = ep < update_horizon ? ep : update_horizon;
+      for (int64_t k = 0; k < back; ++k) {
+        const int64_t i = ((cur - k) % capacity + capacity) % capacity;
+        if (!valid[i]) { valid[i] = 1; ++nvalid; }
+      }
+    }
+  }
+  state[0] = add_count; state[1] = ep; state[2] = nvalid;
+}

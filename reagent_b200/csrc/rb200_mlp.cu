@@ -47,9 +47,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_rows_kernel(const Mlp net
 #define RB200_LAUNCH_FWD(TM_, KC_, grid, smem, stream, ...)                                   \
   do {                                                                                        \
     auto kfn = mlp_fwd_rows_kernel<TM_, KC_>;                                                 \
-    cudaError_t e_ = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                          (int)(smem));                                       \
-    if (e_ != cudaSuccess) return check_cuda(e_, "cudaFuncSetAttribute(mlp_fwd)");            \
+    static size_t configured_ = 0; /* set once (not inside CUDA-graph capture) */            \
+    if (configured_ < (size_t)(smem)) {                                                       \
+      cudaError_t e_ = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            (int)(smem));                                     \
+      if (e_ != cudaSuccess) return check_cuda(e_, "cudaFuncSetAttribute(mlp_fwd)");               \
+      configured_ = (size_t)(smem);                                                           \
+    }                                                                                         \
     kfn<<<grid, kThreads, smem, stream>>>(__VA_ARGS__);                                       \
   } while (0)
 

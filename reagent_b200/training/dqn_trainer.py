@@ -71,6 +71,7 @@ class DQNTrainer(DQNTrainerBaseLightning):
             raise NotImplementedError("batch-constrained q-learning is out of scope of the fused path")
         self._ws = None
         self.all_action_scores = None
+        self._kernel_events = None  # bench hook: list collecting (start, end) events of K2
 
     # ------------------------------------------------------------------
     def configure_optimizers(self):
@@ -152,8 +153,15 @@ class DQNTrainer(DQNTrainerBaseLightning):
         a.loss = ws["loss"].data_ptr()
         a.tile_counter = ws["counter"].data_ptr()
         qd, qtd = self.q_network.arena.desc(), self.q_network_target.arena.desc()
+        ev = self._kernel_events
+        if ev is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = _lib.lib().rb200_dqn_td_step(qd, qtd, a, ws["net"].c, _lib.cur_stream())
         _lib.check(rc, "rb200_dqn_td_step")
+        if ev is not None:
+            e1.record()
+            ev.append((e0, e1))
         if do_backward:
             wgrad(self.q_network.arena, ws["net"], state, B)
         self.all_action_scores = ws["scores"]
@@ -170,12 +178,26 @@ class DQNTrainer(DQNTrainerBaseLightning):
             self._log_dqn(td_loss, training_batch)
         yield self.soft_update_result()
 
-    def train_batch(self, training_batch: rlt.DiscreteDqnInput, batch_idx: int = 0):
+    def train_batch(self, training_batch: rlt.DiscreteDqnInput, batch_idx: int = 0,
+                    process_group=None):
         """Fast path: one full update in 3 launches, Polyak fused into the Adam kernel.
-        Same arithmetic as driving train_step_gen with reagent_b200.training.loop."""
+        Same arithmetic as driving train_step_gen with reagent_b200.training.loop.
+        With `process_group` (data parallel, one rank per GPU, equal shards): the flat
+        gradient is summed over ranks by ONE all-reduce and scaled by 1/world before Adam
+        (every loss is a batch mean)."""
         opts = self.optimizers()
         self._td_step(training_batch)
-        opts[0].fused_step(target=self.q_network_target.arena, tau=self.tau)
+        if process_group is None:
+            opts[0].fused_step(target=self.q_network_target.arena, tau=self.tau)
+        else:
+            import torch.distributed as dist
+
+            from .workspace import reduced_grad
+
+            g = reduced_grad(self.q_network.arena)
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=process_group)
+            opts[0].fused_step(target=self.q_network_target.arena, tau=self.tau, grad=g,
+                               grad_scale=1.0 / dist.get_world_size(process_group))
         self.all_batches_processed += 1
         return self._ws["loss"]
 

@@ -1,0 +1,116 @@
+"""Whole-update CUDA graphs: replay sample -> TD step -> weight gradients -> Adam + Polyak.
+
+`FusedDqnStep` is the public fast path for the reference workflow "rb.sample_transition_batch
+-> trainer_preprocessor -> Lightning optimizer loop" (reagent/gym/datasets/
+replay_buffer_dataset.py:122-133 + reagent/training/reagent_lightning_module.py:108-133):
+per update the host only draws the random numbers (Python's `random` stream for the
+prioritized buffer, torch.randint for the uniform one -- bit-exact index parity with the
+reference), writes them to pinned memory and replays one captured graph that does the
+host->device copy, the 4 kernels and the device->host copy of the loss.
+"""
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..replay_memory.prioritized_replay_buffer import PrioritizedReplayBuffer
+
+
+class FusedDqnStep:
+    def __init__(self, trainer, replay_buffer, batch_size: int, process_group=None,
+                 slots: int = 2):
+        self.trainer = trainer
+        self.rb = replay_buffer
+        self.B = batch_size
+        self.pg = process_group
+        self.prioritized = isinstance(replay_buffer, PrioritizedReplayBuffer)
+        self.dev = replay_buffer._dev()
+        self.A = trainer.num_actions
+        self.slots = []
+        self.k = 0
+        self.h2d_bytes = batch_size * 8
+        self.d2h_bytes = 4
+        replay_buffer._flush()
+        # warm-up outside capture (lazy allocations, cudaFuncSetAttribute, optimizer state)
+        self._one_update(None)
+        torch.cuda.synchronize()
+        for _ in range(slots):
+            self.slots.append(self._capture())
+
+    # -- one update on the current stream ---------------------------------------
+    def _one_update(self, rnd_dev):
+        if rnd_dev is None:
+            batch = self.rb.sample_discrete_dqn_batch(self.B, self.A)
+        elif self.prioritized:
+            batch = self.rb.sample_discrete_dqn_batch(self.B, self.A, query_dev=rnd_dev)
+        else:
+            batch = self.rb.sample_discrete_dqn_batch(self.B, self.A, ranks_dev=rnd_dev)
+        return self.trainer.train_batch(batch, process_group=self.pg)
+
+    def _capture(self):
+        dt = torch.float64 if self.prioritized else torch.int64
+        host = torch.zeros(self.B, dtype=dt).pin_memory()
+        devb = torch.zeros(self.B, dtype=dt, device=self.dev)
+        loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            devb.copy_(host, non_blocking=True)
+            loss = self._one_update(devb)
+            loss_host.copy_(loss.reshape(1), non_blocking=True)
+        return {"graph": g, "host": host, "dev": devb, "loss_host": loss_host,
+                "done": torch.cuda.Event(), "used": False}
+
+    # -- public --------------------------------------------------------------------
+    def step(self) -> torch.Tensor:
+        """One full update.  Returns the pinned host tensor that will hold the loss once the
+        stream reaches the end of this update (call torch.cuda.current_stream().synchronize()
+        or keep going: slots are recycled only after their event completed)."""
+        s = self.slots[self.k % len(self.slots)]
+        self.k += 1
+        if s["used"]:
+            s["done"].synchronize()
+        # bring device mirrors up to date OUTSIDE the captured graph (adds / set_priority)
+        self.rb._flush()
+        if self.prioritized:
+            self.rb.sum_tree.device_heap(self.dev)
+        else:
+            self.rb._ensure_valid_index()
+        if self.prioritized:
+            q, pos, idxs = self.rb.host_queries(self.B)
+            if pos:  # rare retry path: resolved on the host, run this update un-captured
+                qd = torch.from_numpy(q).to(self.dev)
+                batch = self.rb.sample_discrete_dqn_batch(self.B, self.A, query_dev=qd,
+                                                          overrides=(pos, idxs))
+                loss = self.trainer.train_batch(batch, process_group=self.pg)
+                s["loss_host"].copy_(loss.reshape(1), non_blocking=True)
+                s["done"].record()
+                s["used"] = True
+                return s["loss_host"]
+            s["host"].numpy()[:] = q
+        else:
+            n_valid = self.rb._num_valid_indices
+            if n_valid == 0:
+                raise RuntimeError(f"Cannot sample {self.B} since there are no valid indices so far.")
+            torch.randint(n_valid, (self.B,), out=s["host"])
+        s["graph"].replay()
+        s["done"].record()
+        s["used"] = True
+        return s["loss_host"]
+
+
+def capture_device_only(trainer, rb, batch_size, steps, queries_dev, process_group=None):
+    """`steps` consecutive updates in ONE graph with all random numbers already resident in
+    HBM (queries_dev[k] is the k-th update's draw) -- the kernel-only measurement of
+    bench.py.  Returns (graph, list of per-update (start, end) event pairs or None)."""
+    A = trainer.num_actions
+    prioritized = isinstance(rb, PrioritizedReplayBuffer)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for k in range(steps):
+            if prioritized:
+                batch = rb.sample_discrete_dqn_batch(batch_size, A, query_dev=queries_dev[k])
+            else:
+                batch = rb.sample_discrete_dqn_batch(batch_size, A, ranks_dev=queries_dev[k])
+            trainer.train_batch(batch, process_group=process_group)
+    return g
