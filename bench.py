@@ -160,13 +160,31 @@ def cpu_reference_run(steps, warmup, threads=None):
             possible_next_actions_mask=torch.ones(B, A), next_action=None)
         return O.dqn_update(q, qt, adam, batch, gamma=GAMMA, tau=TAU, loss="huber")[0]
 
+    if threads is None:
+        # "all the host threads it can use": small GEMMs get SLOWER when oversubscribed, so
+        # give the reference its best thread count from a short sweep (1 update each)
+        best = None
+        for c in sorted({os.cpu_count(), 64, 32, 16, 8}, reverse=True):
+            if c > os.cpu_count():
+                continue
+            torch.set_num_threads(c)
+            one()
+            t0 = time.perf_counter()
+            one()
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, c)
+        cores = best[1]
+        torch.set_num_threads(cores)
     for _ in range(warmup):
         one()
     t0 = time.perf_counter()
     for _ in range(steps):
         one()
     dt = time.perf_counter() - t0
-    return steps / dt, cores, f"{steps} full updates (PER sample B={B} + DQN update) after {warmup} warm-up", dt / steps * 1e3
+    return (steps / dt, cores,
+            f"{steps} full updates (PER sample B={B} + DQN update) after {warmup} warm-up; "
+            f"torch threads={cores} (best of a sweep over <= {os.cpu_count()} cores)", dt / steps * 1e3)
 
 
 def run_reference(args):

@@ -21,10 +21,10 @@ struct DqnDev {
   int ld_in, ld_h, ld_q;
 };
 
-template <int TM, int KC>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int NT, int TM, int KC>
+__global__ void __launch_bounds__(NT, 1)
 dqn_td_rows_kernel(const Mlp q, const Mlp qt, const DqnDev p) {
-  constexpr int R = 4 * TM;
+  constexpr int R = (NT / 64) * TM;
   extern __shared__ __align__(16) float smem[];
   const rb200_dqn_args_t& a = p.a;
   const int tid = threadIdx.x;
@@ -44,11 +44,11 @@ dqn_td_rows_kernel(const Mlp q, const Mlp qt, const DqnDev p) {
   const int S = q.dims[0], A = q.dims[L];
 
   // ---- TD target on next_state (no grad) ----
-  tile_load_rows<R>(xin, ld_in, a.next_state, S, S, row0, B);
+  tile_load_rows<NT, R>(xin, ld_in, a.next_state, S, S, row0, B);
   __syncthreads();
   if (a.double_q)
-    tile_mlp_fwd<TM, KC>(q, xin, ld_in, hA, hB, ld_h, qa, ld_q, Wst, nullptr, row0, B);
-  tile_mlp_fwd<TM, KC>(qt, xin, ld_in, hA, hB, ld_h, qb, ld_q, Wst, nullptr, row0, B);
+    tile_mlp_fwd<NT, TM, KC>(q, xin, ld_in, hA, hB, ld_h, qa, ld_q, Wst, nullptr, row0, B);
+  tile_mlp_fwd<NT, TM, KC>(qt, xin, ld_in, hA, hB, ld_h, qb, ld_q, Wst, nullptr, row0, B);
   if (tid < R) {
     const int r = tid, row = row0 + r;
     float tgt = 0.f;
@@ -81,11 +81,11 @@ dqn_td_rows_kernel(const Mlp q, const Mlp qt, const DqnDev p) {
   __syncthreads();
 
   // ---- online network on state (with grad): save hidden activations ----
-  tile_load_rows<R>(xin, ld_in, a.state, S, S, row0, B);
+  tile_load_rows<NT, R>(xin, ld_in, a.state, S, S, row0, B);
   __syncthreads();
-  tile_mlp_fwd<TM, KC>(q, xin, ld_in, hA, hB, ld_h, qc, ld_q, Wst,
+  tile_mlp_fwd<NT, TM, KC>(q, xin, ld_in, hA, hB, ld_h, qc, ld_q, Wst,
                        a.do_backward ? p.ws.hidden : nullptr, row0, B);
-  if (a.all_action_scores) tile_store_rows<R>(qc, ld_q, a.all_action_scores, A, A, row0, B);
+  if (a.all_action_scores) tile_store_rows<NT, R>(qc, ld_q, a.all_action_scores, A, A, row0, B);
 
   // ---- loss and d loss / d q_network output ----
   if (tid < R) {
@@ -139,13 +139,13 @@ dqn_td_rows_kernel(const Mlp q, const Mlp qt, const DqnDev p) {
 
   // ---- backward: dZ chain of q_network ----
   if (a.do_backward)
-    tile_mlp_bwd<TM, KC>(q, qa, ld_q, hA, hB, hC, ld_h, Wst, p.ws.hidden, p.ws.dz, row0, B,
+    tile_mlp_bwd<NT, TM, KC>(q, qa, ld_q, hA, hB, hC, ld_h, Wst, p.ws.hidden, p.ws.dz, row0, B,
                          nullptr, 0, 0, 0);
 }
 
-#define RB200_LAUNCH_DQN(TM_, KC_, grid, smem, stream, ...)                                   \
+#define RB200_LAUNCH_DQN(NT_, TM_, KC_, grid, smem, stream, ...)                                   \
   do {                                                                                        \
-    auto kfn = dqn_td_rows_kernel<TM_, KC_>;                                                  \
+    auto kfn = dqn_td_rows_kernel<NT_, TM_, KC_>;                                                  \
     static size_t configured_ = 0; /* set once (not inside CUDA-graph capture) */            \
     if (configured_ < (size_t)(smem)) {                                                       \
       cudaError_t e_ = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -153,7 +153,7 @@ dqn_td_rows_kernel(const Mlp q, const Mlp qt, const DqnDev p) {
       if (e_ != cudaSuccess) return check_cuda(e_, "cudaFuncSetAttribute(dqn)");               \
       configured_ = (size_t)(smem);                                                           \
     }                                                                                         \
-    kfn<<<grid, kThreads, smem, stream>>>(__VA_ARGS__);                                       \
+    kfn<<<grid, NT_, smem, stream>>>(__VA_ARGS__);                                       \
   } while (0)
 
 static RowsCfg dqn_cfg(const rb200_mlp_t* q, int batch, int* ld_q) {
@@ -196,7 +196,7 @@ extern "C" int rb200_dqn_td_step(const rb200_mlp_t* q_net, const rb200_mlp_t* q_
   p.ld_in = cfg.ld_in;
   p.ld_h = cfg.ld_h;
   const Mlp q = make_mlp(q_net), qt = make_mlp(q_target);
-  const int grid = ceil_div(args->batch, 4 * cfg.tm);
+  const int grid = ceil_div(args->batch, rows_per_tile(cfg));
   cudaStream_t st = (cudaStream_t)stream;
   RB200_DISPATCH_ROWS(cfg, RB200_LAUNCH_DQN, grid, cfg.smem_bytes, st, q, qt, p);
   return check_cuda(cudaGetLastError(), "dqn_td_rows_kernel launch");
@@ -205,5 +205,5 @@ extern "C" int rb200_dqn_td_step(const rb200_mlp_t* q_net, const rb200_mlp_t* q_
 extern "C" int rb200_num_row_tiles(int batch, int max_dim_in, int max_dim_hidden) {
   RowsCfg cfg = pick_rows_cfg(batch, max_dim_in, max_dim_hidden, 1, 3, 64, 0);
   if (cfg.tm == 0) return ceil_div(batch, 16);
-  return ceil_div(batch, 4 * cfg.tm);
+  return ceil_div(batch, rows_per_tile(cfg));
 }

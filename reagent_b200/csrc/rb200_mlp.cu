@@ -13,9 +13,9 @@ struct FwdDev {
   int batch, ld_in, ld_h, ld_o;
 };
 
-template <int TM, int KC>
-__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_rows_kernel(const Mlp net, const FwdDev p) {
-  constexpr int R = 4 * TM;
+template <int NT, int TM, int KC>
+__global__ void __launch_bounds__(NT, 1) mlp_fwd_rows_kernel(const Mlp net, const FwdDev p) {
+  constexpr int R = (NT / 64) * TM;
   extern __shared__ __align__(16) float smem[];
   float* Wst = smem;
   float* xin = Wst + 2 * wstage_floats<KC>();
@@ -25,10 +25,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_rows_kernel(const Mlp net
   const int row0 = blockIdx.x * R;
   // cat(in0, in1): in0 occupies columns [0,d0), in1 columns [d0, d0+d1)
   if (p.in1 == nullptr) {
-    tile_load_rows<R>(xin, p.ld_in, p.in0, p.d0, p.d0, row0, p.batch);
+    tile_load_rows<NT, R>(xin, p.ld_in, p.in0, p.d0, p.d0, row0, p.batch);
   } else {
     const int D = p.d0 + p.d1, D4 = round_up4(D);
-    for (int idx = threadIdx.x; idx < R * D4; idx += kThreads) {
+    for (int idx = threadIdx.x; idx < R * D4; idx += NT) {
       const int r = idx / D4, c = idx - r * D4;
       float v = 0.f;
       if (row0 + r < p.batch) {
@@ -39,14 +39,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_rows_kernel(const Mlp net
     }
   }
   __syncthreads();
-  tile_mlp_fwd<TM, KC>(net, xin, p.ld_in, hA, hB, p.ld_h, xo, p.ld_o, Wst, nullptr, row0, p.batch);
+  tile_mlp_fwd<NT, TM, KC>(net, xin, p.ld_in, hA, hB, p.ld_h, xo, p.ld_o, Wst, nullptr, row0, p.batch);
   const int DO = net.dims[net.n_layers];
-  tile_store_rows<R>(xo, p.ld_o, p.out, DO, DO, row0, p.batch);
+  tile_store_rows<NT, R>(xo, p.ld_o, p.out, DO, DO, row0, p.batch);
 }
 
-#define RB200_LAUNCH_FWD(TM_, KC_, grid, smem, stream, ...)                                   \
+#define RB200_LAUNCH_FWD(NT_, TM_, KC_, grid, smem, stream, ...)                                   \
   do {                                                                                        \
-    auto kfn = mlp_fwd_rows_kernel<TM_, KC_>;                                                 \
+    auto kfn = mlp_fwd_rows_kernel<NT_, TM_, KC_>;                                                 \
     static size_t configured_ = 0; /* set once (not inside CUDA-graph capture) */            \
     if (configured_ < (size_t)(smem)) {                                                       \
       cudaError_t e_ = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_rows_kernel(const Mlp net
       if (e_ != cudaSuccess) return check_cuda(e_, "cudaFuncSetAttribute(mlp_fwd)");               \
       configured_ = (size_t)(smem);                                                           \
     }                                                                                         \
-    kfn<<<grid, kThreads, smem, stream>>>(__VA_ARGS__);                                       \
+    kfn<<<grid, NT_, smem, stream>>>(__VA_ARGS__);                                       \
   } while (0)
 
 }  // namespace rb200
@@ -81,7 +81,7 @@ extern "C" int rb200_mlp_forward(const rb200_mlp_t* net, const float* in0, int32
   if (cfg.tm == 0) { set_last_error("rb200_mlp_forward: tile does not fit in shared memory"); return RB200_E_SMEM; }
   p.ld_in = cfg.ld_in; p.ld_h = cfg.ld_h;
   const Mlp m = make_mlp(net);
-  const int grid = ceil_div(batch, 4 * cfg.tm);
+  const int grid = ceil_div(batch, rows_per_tile(cfg));
   cudaStream_t st = (cudaStream_t)stream;
   RB200_DISPATCH_ROWS(cfg, RB200_LAUNCH_FWD, grid, cfg.smem_bytes, st, m, p);
   return check_cuda(cudaGetLastError(), "mlp_fwd_rows_kernel launch");

@@ -234,7 +234,7 @@ class ReplayBuffer:
 
     def _add_transition(self, transition) -> None:
         cursor = self.cursor()
-        if self._stage_n == _STAGE_ROWS:
+        if self._stage_n == min(_STAGE_ROWS, self._replay_capacity):
             self._flush()
         if self._stage_n == 0:
             self._stage_start = cursor

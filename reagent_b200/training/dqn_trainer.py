@@ -159,6 +159,7 @@ class DQNTrainer(DQNTrainerBaseLightning):
             e0.record()
         rc = _lib.lib().rb200_dqn_td_step(qd, qtd, a, ws["net"].c, _lib.cur_stream())
         _lib.check(rc, "rb200_dqn_td_step")
+        self._last_td_call = (qd, qtd, a, ws["net"].c, keep)  # profiling hook (re-launch)
         if ev is not None:
             e1.record()
             ev.append((e0, e1))
