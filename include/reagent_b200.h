@@ -148,6 +148,58 @@ int rb200_dqn_td_step(const rb200_mlp_t* q_net, const rb200_mlp_t* q_target,
                       const rb200_dqn_args_t* args, const rb200_net_ws_t* ws, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* Fused SAC / TD3 updates over row tiles.                                      */
+/* critic step: replaces SACTrainer.train_step_gen's first section              */
+/*   (reagent/training/sac_trainer.py:214-248: actor(s') + get_log_prob, target */
+/*   critics, min, entropy term, target, q1/q2 MSE) or TD3Trainer's             */
+/*   (reagent/training/td3_trainer.py:138-178), plus autograd's backward through*/
+/*   q1 / q2.  loss[0] = q1 loss, loss[1] = q2 loss.                            */
+/* actor step: replaces sac_trainer.py:254-322 (actor loss, alpha loss) or      */
+/*   td3_trainer.py:181-187, plus the backward through the frozen critics into  */
+/*   the actor (reagent/models/actor.py:169-261 for the Gaussian head).         */
+/*   loss[0] = actor loss, loss[1] = alpha loss; alpha_grad[0] = d/d log_alpha. */
+/* `noise_*` are the N(0,1) draws of torch.randn_like in the reference          */
+/* (actor.py:217, td3_trainer.py:141), supplied by the caller.                  */
+/* ------------------------------------------------------------------------- */
+#define RB200_ALGO_SAC 0
+#define RB200_ALGO_TD3 1
+typedef struct rb200_ac_args {
+  int32_t batch;
+  int32_t algo;
+  const float* state;        /* [B,S] */
+  const float* action;       /* [B,A] (critic step) */
+  const float* next_state;   /* [B,S] (critic step) */
+  const float* reward;       /* [B] */
+  const float* not_terminal; /* [B] */
+  const float* noise_next;   /* [B,A] critic step */
+  const float* noise_cur;    /* [B,A] SAC actor step */
+  float gamma;
+  const float* alpha;        /* [1] SAC entropy temperature (device) */
+  const float* log_alpha;    /* [1] SAC (actor step: alpha loss value) or NULL */
+  float target_entropy;
+  int32_t backprop_through_log_prob;
+  float noise_variance, noise_clip; /* TD3 */
+  /* outputs */
+  float* loss_partials;      /* [2 * num tiles] */
+  float* loss;               /* [2] */
+  uint32_t* tile_counter;    /* [1] zero-initialised, self-resetting */
+  float* alpha_grad;         /* [1] or NULL */
+  float* td_target;          /* [B] or NULL */
+  float* next_action_out;    /* [B,A] or NULL: a' (critic step) / pi(s) (actor step) */
+  float* log_prob_out;       /* [B] or NULL (unclamped sum of log-probs) */
+  float* q1_value;           /* [B] or NULL */
+  float* q2_value;           /* [B] or NULL */
+} rb200_ac_args_t;
+
+int rb200_ac_critic_step(const rb200_mlp_t* actor, const rb200_mlp_t* q1, const rb200_mlp_t* q2,
+                         const rb200_mlp_t* q1_target, const rb200_mlp_t* q2_target,
+                         const rb200_ac_args_t* args, const rb200_net_ws_t* ws_q1,
+                         const rb200_net_ws_t* ws_q2, void* stream);
+int rb200_ac_actor_step(const rb200_mlp_t* actor, const rb200_mlp_t* q1, const rb200_mlp_t* q2,
+                        const rb200_ac_args_t* args, const rb200_net_ws_t* ws_actor,
+                        const rb200_net_ws_t* ws_q1, const rb200_net_ws_t* ws_q2, void* stream);
+
+/* ------------------------------------------------------------------------- */
 /* Weight gradients: dW_l = dZ_l^T . A_{l-1}, db_l = sum_b dZ_l, split over    */
 /* the batch; partial s lands at gpart + s*n_params (arena layout).            */
 /* Replaces autograd's Linear backward (torch) reached from                    */
@@ -181,6 +233,8 @@ typedef struct rb200_adam_args {
   float* target;          /* [n] or NULL: fused Polyak update */
   float tau;
   float one_minus_tau;    /* float(1.0 - tau) computed in double on the host */
+  float* exp_out;         /* [n] or NULL: exp(new param) (SAC: entropy_temperature =
+                             log_alpha.exp(), sac_trainer.py:322) */
 } rb200_adam_args_t;
 int rb200_adam_soft_update(const rb200_adam_args_t* a, void* stream);
 /* stand-alone Polyak update (SoftUpdate.step when not fused) */

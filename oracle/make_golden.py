@@ -271,6 +271,165 @@ def preprocessor_case(name, seed=0, B=64):
     _save(name, arrays, dict(kind="preprocessor", spec={str(k): v for k, v in spec.items()}, B=B))
 
 
+# ---------------------------------------------------------------------------
+# SAC / TD3: torch.randn_like is patched so that the noise draws are recorded
+# ---------------------------------------------------------------------------
+class _NoiseRecorder:
+    def __init__(self, seed):
+        self.gen = torch.Generator().manual_seed(seed)
+        self.log = []
+        self._orig = torch.randn_like
+
+    def __enter__(self):
+        def fake(t, **kw):
+            n = torch.randn(t.shape, generator=self.gen, dtype=t.dtype)
+            self.log.append(n)
+            return n
+        torch.randn_like = fake
+        return self
+
+    def __exit__(self, *a):
+        torch.randn_like = self._orig
+
+
+def _perturb(module, scale=0.1):
+    with torch.no_grad():
+        for _, b in _fc_params(module):
+            b.normal_(0, scale)
+
+
+def _policy_batch(rlt, B, S, A, seed):
+    g = torch.Generator().manual_seed(seed)
+    batch = dict(state=torch.randn(B, S, generator=g), next_state=torch.randn(B, S, generator=g),
+                 action=torch.rand(B, A, generator=g) * 1.98 - 0.99,
+                 next_action=torch.rand(B, A, generator=g) * 1.98 - 0.99,
+                 reward=torch.randn(B, 1, generator=g),
+                 not_terminal=(torch.rand(B, 1, generator=g) > 0.2).float())
+    rb = rlt.PolicyNetworkInput(
+        state=rlt.FeatureData(batch["state"]), next_state=rlt.FeatureData(batch["next_state"]),
+        action=rlt.FeatureData(batch["action"]), next_action=rlt.FeatureData(batch["next_action"]),
+        reward=batch["reward"], not_terminal=batch["not_terminal"], step=None, time_diff=None,
+        extras=rlt.ExtraData())
+    return batch, rb
+
+
+def sac_case(name, *, B=40, S=10, A=3, sizes=(16, 12), acts=("relu", "relu"), twin=True,
+             learn_alpha=True, gamma=0.95, tau=0.05, lr=3e-3, entropy_temperature=0.2,
+             target_entropy=-1.5, backprop=True, seed=0, n_updates=3):
+    rlt = ref("reagent.core.types")
+    params = ref("reagent.core.parameters")
+    actor_mod = ref("reagent.models.actor")
+    critic_mod = ref("reagent.models.critic")
+    tr = ref("reagent.training.sac_trainer")
+    union = ref("reagent.optimizer.union")
+    torch.manual_seed(seed)
+    actor = actor_mod.GaussianFullyConnectedActor(S, A, list(sizes), list(acts))
+    q1 = critic_mod.FullyConnectedCritic(S, A, list(sizes), list(acts))
+    q2 = critic_mod.FullyConnectedCritic(S, A, list(sizes), list(acts)) if twin else None
+    for m in (actor, q1, q2):
+        if m is not None:
+            _perturb(m)
+    opt = lambda: union.Optimizer__Union(Adam=union.classes["Adam"](lr=lr))  # noqa: E731
+    trainer = tr.SACTrainer(
+        actor, q1, q2, rl=params.RLParameters(gamma=gamma, target_update_rate=tau),
+        q_network_optimizer=opt(), actor_network_optimizer=opt(),
+        alpha_optimizer=opt() if learn_alpha else None, minibatch_size=B,
+        entropy_temperature=entropy_temperature, target_entropy=target_entropy,
+        backprop_through_log_prob=backprop)
+    batch, rb = _policy_batch(rlt, B, S, A, seed + 1)
+    arrays = {f"batch.{k}": _np(v) for k, v in batch.items()}
+    _dump_net(arrays, "actor0", actor)
+    _dump_net(arrays, "q1_0", q1)
+    if twin:
+        _dump_net(arrays, "q2_0", q2)
+    opts = [o["optimizer"] for o in trainer.configure_optimizers()]
+    all_losses = []
+    with _NoiseRecorder(seed + 2) as rec:
+        for it in range(n_updates):
+            cap = {}
+            n0 = len(rec.log)
+            losses = run_update(trainer, rb, it, opts, capture=cap)
+            assert len(rec.log) - n0 == 2, len(rec.log) - n0
+            arrays[f"noise{it}.next"] = _np(rec.log[n0])
+            arrays[f"noise{it}.cur"] = _np(rec.log[n0 + 1])
+            all_losses.append([np.nan if l is None else l for l in losses[:-1]])
+            if it == 0:
+                for oi, gl in cap.items():
+                    for pi, g in enumerate(gl):
+                        if g is not None:
+                            arrays[f"grad0.opt{oi}.{pi}"] = _np(g)
+    arrays["losses"] = np.array(all_losses, dtype=np.float64)
+    _dump_net(arrays, "actorN", actor)
+    _dump_net(arrays, "q1_N", q1)
+    _dump_net(arrays, "q1t_N", trainer.q1_network_target)
+    if twin:
+        _dump_net(arrays, "q2_N", q2)
+        _dump_net(arrays, "q2t_N", trainer.q2_network_target)
+    if learn_alpha:
+        arrays["log_alpha_N"] = _np(trainer.log_alpha)
+    meta = dict(kind="sac", B=B, S=S, A=A, sizes=list(sizes), acts=list(acts), twin=twin,
+                learn_alpha=learn_alpha, gamma=gamma, tau=tau, lr=lr,
+                entropy_temperature=entropy_temperature, target_entropy=target_entropy,
+                backprop=backprop, n_updates=n_updates)
+    _save(name, arrays, meta)
+
+
+def td3_case(name, *, B=40, S=10, A=3, sizes=(16, 12), acts=("relu", "relu"), twin=True,
+             gamma=0.95, tau=0.05, lr=3e-3, noise_variance=0.2, noise_clip=0.5, delay=2, seed=0,
+             n_updates=3):
+    rlt = ref("reagent.core.types")
+    params = ref("reagent.core.parameters")
+    actor_mod = ref("reagent.models.actor")
+    critic_mod = ref("reagent.models.critic")
+    tr = ref("reagent.training.td3_trainer")
+    union = ref("reagent.optimizer.union")
+    torch.manual_seed(seed)
+    actor = actor_mod.FullyConnectedActor(S, A, list(sizes), list(acts))
+    q1 = critic_mod.FullyConnectedCritic(S, A, list(sizes), list(acts))
+    q2 = critic_mod.FullyConnectedCritic(S, A, list(sizes), list(acts)) if twin else None
+    for m in (actor, q1, q2):
+        if m is not None:
+            _perturb(m)
+    opt = lambda: union.Optimizer__Union(Adam=union.classes["Adam"](lr=lr))  # noqa: E731
+    trainer = tr.TD3Trainer(
+        actor, q1, q2, rl=params.RLParameters(gamma=gamma, target_update_rate=tau),
+        q_network_optimizer=opt(), actor_network_optimizer=opt(), minibatch_size=B,
+        noise_variance=noise_variance, noise_clip=noise_clip, delayed_policy_update=delay)
+    batch, rb = _policy_batch(rlt, B, S, A, seed + 1)
+    arrays = {f"batch.{k}": _np(v) for k, v in batch.items()}
+    _dump_net(arrays, "actor0", actor)
+    _dump_net(arrays, "q1_0", q1)
+    if twin:
+        _dump_net(arrays, "q2_0", q2)
+    opts = [o["optimizer"] for o in trainer.configure_optimizers()]
+    all_losses = []
+    with _NoiseRecorder(seed + 2) as rec:
+        for it in range(n_updates):
+            cap = {}
+            n0 = len(rec.log)
+            losses = run_update(trainer, rb, it, opts, capture=cap)
+            assert len(rec.log) - n0 == 1
+            arrays[f"noise{it}.next"] = _np(rec.log[n0])
+            all_losses.append([np.nan if l is None else l for l in losses[:-1]])
+            if it == 0:
+                for oi, gl in cap.items():
+                    for pi, g in enumerate(gl):
+                        if g is not None:
+                            arrays[f"grad0.opt{oi}.{pi}"] = _np(g)
+    arrays["losses"] = np.array(all_losses, dtype=np.float64)
+    _dump_net(arrays, "actorN", actor)
+    _dump_net(arrays, "actort_N", trainer.actor_network_target)
+    _dump_net(arrays, "q1_N", q1)
+    _dump_net(arrays, "q1t_N", trainer.q1_network_target)
+    if twin:
+        _dump_net(arrays, "q2_N", q2)
+        _dump_net(arrays, "q2t_N", trainer.q2_network_target)
+    meta = dict(kind="td3", B=B, S=S, A=A, sizes=list(sizes), acts=list(acts), twin=twin,
+                gamma=gamma, tau=tau, lr=lr, noise_variance=noise_variance,
+                noise_clip=noise_clip, delay=delay, n_updates=n_updates)
+    _save(name, arrays, meta)
+
+
 def main():
     dqn_case("dqn_huber_double")
     dqn_case("dqn_mse_single_masked", loss="mse", double_q=False, random_masks=True, seed=1)
@@ -291,6 +450,11 @@ def main():
     replay_case("replay_per_big", prioritized=True, cap=4096, n_add=6000, B=256, horizon=1,
                 seed=6, S=8, n_samples=2)
     preprocessor_case("preprocessor_all_types")
+    sac_case("sac_twin_alpha")
+    sac_case("sac_single_fixed_alpha", twin=False, learn_alpha=False, seed=3, acts=("tanh", "leaky_relu"))
+    sac_case("sac_twin_odd_dims", B=37, S=7, A=2, sizes=(10,), acts=("relu",), seed=5, backprop=False)
+    td3_case("td3_twin")
+    td3_case("td3_single", twin=False, seed=3, acts=("tanh", "relu"), delay=3)
 
 
 if __name__ == "__main__":

@@ -153,3 +153,170 @@ def dqn_update(q: Net, qt: Net, adam: AdamState, batch, *, gamma, tau, **kw):
     adam.step(params, grads)
     soft_update(qt, q, tau)
     return float(loss.detach()), grads, aux
+
+
+# ---------------------------------------------------------------------------
+# Gaussian actor head (reagent/models/actor.py:169-261)
+# ---------------------------------------------------------------------------
+LOG_PROB_MIN, LOG_PROB_MAX = -2.0, 2.0
+_ACT_EPS = 1e-6
+_CONST = math.log(math.sqrt(2 * math.pi))
+
+
+def gaussian_log_prob(actor: Net, state, squashed_action):
+    """GaussianFullyConnectedActor.get_log_prob (actor.py:233-261)."""
+    out = mlp(actor, state)
+    A = out.shape[1] // 2
+    loc, scale_log = out[:, :A], out[:, A:].clamp(LOG_PROB_MIN, LOG_PROB_MAX)
+    raw_action = torch.atanh(squashed_action)
+    r = (raw_action - loc) / scale_log.exp()
+    log_prob = -(r ** 2) / 2 - scale_log - _CONST
+    squash_correction = (1 - squashed_action ** 2 + _ACT_EPS).log()
+    return torch.sum(log_prob - squash_correction, dim=1).reshape(-1, 1)
+
+
+def gaussian_actor_forward(actor: Net, state, noise):
+    """GaussianFullyConnectedActor.forward with the randn_like draw injected (actor.py:215-231)."""
+    out = mlp(actor, state)
+    A = out.shape[1] // 2
+    loc, scale_log = out[:, :A], out[:, A:].clamp(LOG_PROB_MIN, LOG_PROB_MAX)
+    raw_action = loc + noise * scale_log.exp()
+    squashed = torch.clamp(torch.tanh(raw_action), -1.0 + _ACT_EPS, 1.0 - _ACT_EPS)
+    return squashed, gaussian_log_prob(actor, state, squashed)
+
+
+def critic(q: Net, state, action):
+    """FullyConnectedCritic.forward (reagent/models/critic.py:76-92)."""
+    return mlp(q, torch.cat((state, action), dim=-1))
+
+
+def _grad_step(loss, net_or_params, adam):
+    params = net_or_params if isinstance(net_or_params, list) else net_params(net_or_params)
+    grads = torch.autograd.grad(loss, params)
+    grads = [g.detach().clone() for g in grads]
+    adam.step(params, grads)
+    return grads
+
+
+class SacState:
+    """Mutable state of the restated SACTrainer (twin or single critic, no value net)."""
+
+    def __init__(self, actor, q1, q2, *, lr=1e-3, entropy_temperature=0.01, learn_alpha=True,
+                 target_entropy=-1.0):
+        self.actor, self.q1, self.q2 = actor, q1, q2
+        self.q1t = clone_net(q1)
+        self.q2t = None if q2 is None else clone_net(q2)
+        for n in (actor, q1, q2):
+            if n is not None:
+                for p in net_params(n):
+                    p.requires_grad_(True)
+        self.alpha = entropy_temperature
+        self.learn_alpha = learn_alpha
+        self.target_entropy = target_entropy
+        self.adam_q1 = AdamState(net_params(q1), lr=lr)
+        self.adam_q2 = None if q2 is None else AdamState(net_params(q2), lr=lr)
+        self.adam_actor = AdamState(net_params(actor), lr=lr)
+        if learn_alpha:
+            # float64, as torch.tensor([np.log(x)]) is in the reference (sac_trainer.py:122-126)
+            self.log_alpha = torch.tensor([math.log(entropy_temperature)], dtype=torch.float64,
+                                          requires_grad=True)
+            self.adam_alpha = AdamState([self.log_alpha], lr=lr)
+
+
+def sac_update(st: SacState, batch, noise_next, noise_cur, *, gamma, tau,
+               backprop_through_log_prob=True):
+    """One SACTrainer update (reagent/training/sac_trainer.py:195-385, value_network=None).
+    Returns dict(losses=[q1, q2, actor, alpha], grads={...})."""
+    state, action = batch["state"], batch["action"]
+    reward, not_done = batch["reward"], batch["not_terminal"].float()
+    # --- target (:214-239) ---
+    a_next, _ = gaussian_actor_forward(st.actor, batch["next_state"], noise_next)
+    next_v = critic(st.q1t, batch["next_state"], a_next)
+    if st.q2 is not None:
+        next_v = torch.min(next_v, critic(st.q2t, batch["next_state"], a_next))
+    log_prob_a = gaussian_log_prob(st.actor, batch["next_state"], a_next).clamp(
+        LOG_PROB_MIN, LOG_PROB_MAX)
+    next_v = (next_v - st.alpha * log_prob_a).float()
+    discount = torch.full_like(reward, gamma)
+    target = (reward + discount * next_v * not_done) if gamma > 0.0 else reward
+    target = target.detach()
+    out = {"losses": [], "grads": {}, "target": target}
+    # --- critics (:241-248) ---
+    q1_loss = F.mse_loss(critic(st.q1, state, action), target)
+    out["grads"]["q1"] = _grad_step(q1_loss, st.q1, st.adam_q1)
+    out["losses"].append(float(q1_loss))
+    if st.q2 is not None:
+        q2_loss = F.mse_loss(critic(st.q2, state, action), target)
+        out["grads"]["q2"] = _grad_step(q2_loss, st.q2, st.adam_q2)
+        out["losses"].append(float(q2_loss))
+    # --- actor (:254-308), sees the updated critics ---
+    a_cur, logp = gaussian_actor_forward(st.actor, state, noise_cur)
+    min_q = critic(st.q1, state, a_cur)
+    if st.q2 is not None:
+        min_q = torch.min(min_q, critic(st.q2, state, a_cur))
+    actor_log_prob = logp.clamp(LOG_PROB_MIN, LOG_PROB_MAX)
+    if not backprop_through_log_prob:
+        actor_log_prob = actor_log_prob.detach()
+    actor_loss = (st.alpha * actor_log_prob - min_q).mean()
+    out["grads"]["actor"] = _grad_step(actor_loss, st.actor, st.adam_actor)
+    out["losses"].append(float(actor_loss))
+    # --- alpha (:311-322) ---
+    if st.learn_alpha:
+        alpha_loss = -(
+            (st.log_alpha * (logp.clamp(LOG_PROB_MIN, LOG_PROB_MAX) + st.target_entropy).detach())
+            .mean())
+        out["grads"]["alpha"] = _grad_step(alpha_loss, [st.log_alpha], st.adam_alpha)
+        out["losses"].append(float(alpha_loss))
+        st.alpha = st.log_alpha.detach().exp()
+    # --- soft update (:383-385) ---
+    soft_update(st.q1t, st.q1, tau)
+    if st.q2 is not None:
+        soft_update(st.q2t, st.q2, tau)
+    return out
+
+
+class Td3State:
+    def __init__(self, actor, q1, q2, *, lr=1e-3):
+        self.actor, self.q1, self.q2 = actor, q1, q2
+        self.actor_t, self.q1t = clone_net(actor), clone_net(q1)
+        self.q2t = None if q2 is None else clone_net(q2)
+        for n in (actor, q1, q2):
+            if n is not None:
+                for p in net_params(n):
+                    p.requires_grad_(True)
+        self.adam_q1 = AdamState(net_params(q1), lr=lr)
+        self.adam_q2 = None if q2 is None else AdamState(net_params(q2), lr=lr)
+        self.adam_actor = AdamState(net_params(actor), lr=lr)
+
+
+def td3_update(st: Td3State, batch, noise_next, batch_idx, *, gamma, tau, noise_variance=0.2,
+               noise_clip=0.5, delayed_policy_update=2):
+    """One TD3Trainer update (reagent/training/td3_trainer.py:125-199)."""
+    state, action = batch["state"], batch["action"]
+    with torch.no_grad():  # :138-153
+        next_actor = mlp(st.actor_t, batch["next_state"])
+        noise = noise_next * noise_variance
+        next_actor = (next_actor + noise.clamp(-noise_clip, noise_clip)).clamp(-1.0, 1.0)
+        next_q = critic(st.q1t, batch["next_state"], next_actor)
+        if st.q2 is not None:
+            next_q = torch.min(next_q, critic(st.q2t, batch["next_state"], next_actor))
+        target = batch["reward"] + gamma * next_q * batch["not_terminal"].float()
+    out = {"losses": [], "grads": {}, "target": target}
+    q1_loss = F.mse_loss(critic(st.q1, state, action), target)
+    out["grads"]["q1"] = _grad_step(q1_loss, st.q1, st.adam_q1)
+    out["losses"].append(float(q1_loss))
+    if st.q2 is not None:
+        q2_loss = F.mse_loss(critic(st.q2, state, action), target)
+        out["grads"]["q2"] = _grad_step(q2_loss, st.q2, st.adam_q2)
+        out["losses"].append(float(q2_loss))
+    if batch_idx % delayed_policy_update == 0:  # :181-194
+        actor_loss = -(critic(st.q1, state, mlp(st.actor, state)).mean())
+        out["grads"]["actor"] = _grad_step(actor_loss, st.actor, st.adam_actor)
+        out["losses"].append(float(actor_loss))
+        soft_update(st.q1t, st.q1, tau)
+        if st.q2 is not None:
+            soft_update(st.q2t, st.q2, tau)
+        soft_update(st.actor_t, st.actor, tau)
+    else:
+        out["losses"].append(None)
+    return out

@@ -84,6 +84,24 @@ class AdamArgsT(C.Structure):
         ("target", _vp),
         ("tau", C.c_float),
         ("one_minus_tau", C.c_float),
+        ("exp_out", _vp),
+    ]
+
+
+ALGO_SAC, ALGO_TD3 = 0, 1
+
+
+class AcArgsT(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("algo", C.c_int32),
+        ("state", _vp), ("action", _vp), ("next_state", _vp), ("reward", _vp),
+        ("not_terminal", _vp), ("noise_next", _vp), ("noise_cur", _vp),
+        ("gamma", C.c_float), ("alpha", _vp), ("log_alpha", _vp),
+        ("target_entropy", C.c_float), ("backprop_through_log_prob", C.c_int32),
+        ("noise_variance", C.c_float), ("noise_clip", C.c_float),
+        ("loss_partials", _vp), ("loss", _vp), ("tile_counter", _vp), ("alpha_grad", _vp),
+        ("td_target", _vp), ("next_action_out", _vp), ("log_prob_out", _vp),
+        ("q1_value", _vp), ("q2_value", _vp),
     ]
 
 
@@ -155,6 +173,12 @@ def _declare(lib):
     lib.rb200_sumtree_sample_host.restype = C.c_int64
     lib.rb200_replay_add_batch_host.argtypes = [_vp, C.c_int64, C.c_int64, C.c_int32, _vp, _vp, _vp]
     lib.rb200_replay_add_batch_host.restype = None
+    lib.rb200_ac_critic_step.argtypes = [C.POINTER(MlpT), C.POINTER(MlpT), C.POINTER(MlpT),
+                                         C.POINTER(MlpT), C.POINTER(MlpT), C.POINTER(AcArgsT),
+                                         C.POINTER(NetWsT), C.POINTER(NetWsT), _vp]
+    lib.rb200_ac_actor_step.argtypes = [C.POINTER(MlpT), C.POINTER(MlpT), C.POINTER(MlpT),
+                                        C.POINTER(AcArgsT), C.POINTER(NetWsT), C.POINTER(NetWsT),
+                                        C.POINTER(NetWsT), _vp]
     lib.rb200_wgrad_splits.argtypes = [C.c_int]
     lib.rb200_mlp_wgrad.argtypes = [C.POINTER(MlpT), _vp, C.c_int32, C.POINTER(NetWsT), _vp,
                                     C.c_int32, _vp]

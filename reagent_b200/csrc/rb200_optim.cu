@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(256) adam_soft_kernel(const AdamDev d) {
     a.params[i] = p;
     a.exp_avg[i] = m;
     a.exp_avg_sq[i] = v;
+    if (a.exp_out) a.exp_out[i] = expf(p);
     if (a.target) {
       const float tg = a.target[i];
       a.target[i] = __fadd_rn(__fmul_rn(a.tau, p), __fmul_rn(a.one_minus_tau, tg));

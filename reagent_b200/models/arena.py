@@ -104,12 +104,21 @@ def arena_of(params) -> ParamArena:
 
 
 class ScalarArena(ParamArena):
-    """Arena wrapping one stand-alone contiguous parameter (e.g. SAC's log_alpha)."""
+    """Arena wrapping one stand-alone contiguous parameter (e.g. SAC's log_alpha).  `flat`
+    follows the parameter when the owning module is moved between devices."""
 
     def __init__(self, param: torch.nn.Parameter):
         self.dims, self.acts, self.w_off, self.b_off = [], [], [], []
         self.n = param.numel()
-        self.flat = param.data.view(-1)
+        self._param = param
         self.gpart = None
         self.grad_ready = False
         param._rb200_arena = self
+
+    @property
+    def flat(self):
+        return self._param.data.view(-1)
+
+    @flat.setter
+    def flat(self, v):
+        pass

@@ -67,7 +67,8 @@ class FusedAdam(torch.optim.Optimizer):
     # ------------------------------------------------------------------
     @torch.no_grad()
     def fused_step(self, target: Optional[ParamArena] = None, tau: float = 0.0,
-                   grad: Optional[torch.Tensor] = None, grad_scale: float = 1.0):
+                   grad: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
+                   exp_out: Optional[torch.Tensor] = None):
         """Adam step (+ Polyak update of `target` with the NEW parameters when given)."""
         self._ensure_state()
         a = self.arena
@@ -103,6 +104,7 @@ class FusedAdam(torch.optim.Optimizer):
             args.target = None
             args.tau = 0.0
             args.one_minus_tau = 1.0
+        args.exp_out = None if exp_out is None else exp_out.data_ptr()
         _lib.check(_lib.lib().rb200_adam_soft_update(args, _lib.cur_stream()),
                    "rb200_adam_soft_update")
         a.grad_ready = False

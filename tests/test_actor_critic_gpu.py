@@ -1,0 +1,277 @@
+"""GPU parity of the fused SAC / TD3 updates vs golden vectors from the unmodified
+reference trainers (noise draws injected) and vs the CPU oracle at BASELINE config sizes.
+Tolerance 1e-5 relative fp32 (north star); SAC's actor gradients pass through
+atanh(tanh(x)), whose fp32 round trip is ill-conditioned near saturation, and get 5e-5."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import td_oracle as O
+from tests import golden_util as G
+from tests.test_oracle_golden import SAC_CASES, TD3_CASES
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _pbatch(b):
+    from reagent_b200.core import types as rlt
+
+    return rlt.PolicyNetworkInput(
+        state=rlt.FeatureData(b["state"]), next_state=rlt.FeatureData(b["next_state"]),
+        action=rlt.FeatureData(b["action"]), next_action=rlt.FeatureData(b["next_action"]),
+        reward=b["reward"], not_terminal=b["not_terminal"], step=None, time_diff=None,
+        extras=rlt.ExtraData())
+
+
+def _cmp_module(mod, arrays, prefix, tol=TOL):
+    for i, seq in enumerate(mod.fc.dnn):
+        assert G.rel_err(seq[0].weight, arrays[f"{prefix}.W{i}"]) < tol, f"{prefix}.W{i}"
+        assert G.rel_err(seq[0].bias, arrays[f"{prefix}.b{i}"]) < tol, f"{prefix}.b{i}"
+
+
+def _build_sac(meta, arrays):
+    from reagent_b200.core.parameters import RLParameters
+    from reagent_b200.models import FullyConnectedCritic, GaussianFullyConnectedActor
+    from reagent_b200.optimizer import Optimizer__Union
+    from reagent_b200.training import SACTrainer
+
+    S, A = meta["S"], meta["A"]
+    actor = GaussianFullyConnectedActor(S, A, meta["sizes"], meta["acts"])
+    q1 = FullyConnectedCritic(S, A, meta["sizes"], meta["acts"])
+    q2 = FullyConnectedCritic(S, A, meta["sizes"], meta["acts"]) if meta["twin"] else None
+    G.load_into_module(arrays, "actor0", actor)
+    G.load_into_module(arrays, "q1_0", q1)
+    if q2 is not None:
+        G.load_into_module(arrays, "q2_0", q2)
+    opt = lambda: Optimizer__Union.default(lr=meta["lr"])  # noqa: E731
+    kw = {} if meta["learn_alpha"] else {"alpha_optimizer": None}
+    t = SACTrainer(actor, q1, q2, rl=RLParameters(gamma=meta["gamma"], target_update_rate=meta["tau"]),
+                   q_network_optimizer=opt(), actor_network_optimizer=opt(),
+                   minibatch_size=meta["B"], entropy_temperature=meta["entropy_temperature"],
+                   target_entropy=meta["target_entropy"],
+                   backprop_through_log_prob=meta["backprop"],
+                   **({"alpha_optimizer": opt()} if meta["learn_alpha"] else kw))
+    return t.cuda()
+
+
+def _inject(t, arrays, it):
+    def hook(name, shape, device):
+        return torch.from_numpy(arrays[f"noise{it}.{name}"]).to(device)
+    t.noise_hook = hook
+
+
+def _check_sac_final(t, arrays, meta):
+    _cmp_module(t.actor_network, arrays, "actorN", 2e-5)
+    _cmp_module(t.q1_network, arrays, "q1_N")
+    _cmp_module(t.q1_network_target, arrays, "q1t_N")
+    if meta["twin"]:
+        _cmp_module(t.q2_network, arrays, "q2_N")
+        _cmp_module(t.q2_network_target, arrays, "q2t_N")
+    if meta["learn_alpha"]:
+        assert G.rel_err(t.log_alpha, arrays["log_alpha_N"]) < TOL
+
+
+@pytest.mark.parametrize("name", SAC_CASES)
+def test_sac_generator_path_matches_reference(name):
+    from reagent_b200.training import run_update
+
+    arrays, meta = G.load(name)
+    t = _build_sac(meta, arrays)
+    batch = _pbatch(G.batch_tensors(arrays, "cuda"))
+    for it in range(meta["n_updates"]):
+        _inject(t, arrays, it)
+        if it == 0:
+            opts = t.optimizers()
+            nets = [t.q1_network] + ([t.q2_network] if meta["twin"] else []) + [t.actor_network]
+            for oi, opt in enumerate(opts):
+                loss = t.training_step(batch, it, oi)
+                if oi < len(nets):
+                    tol = 5e-5 if nets[oi] is t.actor_network else TOL
+                    for pi, g in enumerate(t.net_grads(nets[oi])):
+                        assert G.rel_err(g, arrays[f"grad0.opt{oi}.{pi}"]) < tol, (oi, pi)
+                elif meta["learn_alpha"] and oi == len(nets):
+                    assert G.rel_err(t._ws["alpha_grad"], arrays[f"grad0.opt{oi}.0"]) < TOL
+                if oi < len(opts) - 1:
+                    ref = arrays["losses"][it][oi]
+                    assert abs(float(loss.detach()) - ref) <= TOL * max(1.0, abs(ref)), (oi, float(loss.detach()), ref)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+        else:
+            losses = run_update(t, batch, it)
+            for oi, ref in enumerate(arrays["losses"][it]):
+                assert abs(float(losses[oi].detach()) - ref) <= 2e-5 * max(1.0, abs(ref)), (it, oi)
+    _check_sac_final(t, arrays, meta)
+
+
+@pytest.mark.parametrize("name", SAC_CASES)
+def test_sac_fast_path_matches_reference(name):
+    arrays, meta = G.load(name)
+    t = _build_sac(meta, arrays)
+    batch = _pbatch(G.batch_tensors(arrays, "cuda"))
+    for it in range(meta["n_updates"]):
+        _inject(t, arrays, it)
+        closs, aloss = t.train_batch(batch, it)
+        ref = arrays["losses"][it]
+        assert abs(float(closs[0]) - ref[0]) <= 2e-5 * max(1.0, abs(ref[0]))
+    _check_sac_final(t, arrays, meta)
+
+
+def _build_td3(meta, arrays):
+    from reagent_b200.core.parameters import RLParameters
+    from reagent_b200.models import FullyConnectedActor, FullyConnectedCritic
+    from reagent_b200.optimizer import Optimizer__Union
+    from reagent_b200.training import TD3Trainer
+
+    S, A = meta["S"], meta["A"]
+    actor = FullyConnectedActor(S, A, meta["sizes"], meta["acts"])
+    q1 = FullyConnectedCritic(S, A, meta["sizes"], meta["acts"])
+    q2 = FullyConnectedCritic(S, A, meta["sizes"], meta["acts"]) if meta["twin"] else None
+    G.load_into_module(arrays, "actor0", actor)
+    G.load_into_module(arrays, "q1_0", q1)
+    if q2 is not None:
+        G.load_into_module(arrays, "q2_0", q2)
+    opt = lambda: Optimizer__Union.default(lr=meta["lr"])  # noqa: E731
+    t = TD3Trainer(actor, q1, q2, rl=RLParameters(gamma=meta["gamma"], target_update_rate=meta["tau"]),
+                   q_network_optimizer=opt(), actor_network_optimizer=opt(),
+                   minibatch_size=meta["B"], noise_variance=meta["noise_variance"],
+                   noise_clip=meta["noise_clip"], delayed_policy_update=meta["delay"])
+    return t.cuda()
+
+
+def _check_td3_final(t, arrays, meta):
+    _cmp_module(t.actor_network, arrays, "actorN")
+    _cmp_module(t.actor_network_target, arrays, "actort_N")
+    _cmp_module(t.q1_network, arrays, "q1_N")
+    _cmp_module(t.q1_network_target, arrays, "q1t_N")
+    if meta["twin"]:
+        _cmp_module(t.q2_network, arrays, "q2_N")
+        _cmp_module(t.q2_network_target, arrays, "q2t_N")
+
+
+@pytest.mark.parametrize("name", TD3_CASES)
+@pytest.mark.parametrize("fast", [False, True])
+def test_td3_matches_reference(name, fast):
+    from reagent_b200.training import run_update
+
+    arrays, meta = G.load(name)
+    t = _build_td3(meta, arrays)
+    batch = _pbatch(G.batch_tensors(arrays, "cuda"))
+    for it in range(meta["n_updates"]):
+        _inject(t, arrays, it)
+        ref = arrays["losses"][it]
+        if fast:
+            closs, aloss = t.train_batch(batch, it)
+            assert abs(float(closs[0]) - ref[0]) <= TOL * max(1.0, abs(ref[0]))
+            assert (aloss is None) == bool(np.isnan(ref[-1]))
+        else:
+            if it == 0:
+                opts = t.optimizers()
+                nets = [t.q1_network] + ([t.q2_network] if meta["twin"] else []) + [t.actor_network]
+                for oi, opt in enumerate(opts):
+                    loss = t.training_step(batch, it, oi)
+                    if oi < len(nets):
+                        for pi, g in enumerate(t.net_grads(nets[oi])):
+                            assert G.rel_err(g, arrays[f"grad0.opt{oi}.{pi}"]) < TOL, (oi, pi)
+                    opt.zero_grad()
+                    loss.backward()
+                    opt.step()
+            else:
+                losses = run_update(t, batch, it)
+                for oi, r in enumerate(ref):
+                    if np.isnan(r):
+                        assert losses[oi] is None
+                    else:
+                        assert abs(float(losses[oi].detach()) - r) <= TOL * max(1.0, abs(r))
+    _check_td3_final(t, arrays, meta)
+
+
+def _rand_net(dims, acts, gen, bias=0.05):
+    n = O.make_net(dims, acts, gen)
+    for b in n["b"]:
+        b.copy_(torch.randn(b.shape, generator=gen) * bias)
+    return n
+
+
+def _net_arrays(arrays, prefix, net):
+    for i in range(len(net["W"])):
+        arrays[f"{prefix}.W{i}"] = net["W"][i].detach().numpy().copy()
+        arrays[f"{prefix}.b{i}"] = net["b"][i].detach().numpy().copy()
+
+
+def test_sac_config4_shard_matches_oracle():
+    """BASELINE config 4 per-GPU shard: S=256, A=32, B=2048, [256,256] nets, twin critics."""
+    S, A, B = 256, 32, 2048
+    meta = dict(S=S, A=A, B=B, sizes=[256, 256], acts=["relu", "relu"], twin=True,
+                learn_alpha=True, gamma=0.99, tau=0.005, lr=1e-3, entropy_temperature=0.1,
+                target_entropy=-float(A), backprop=True, n_updates=2)
+    gen = torch.Generator().manual_seed(0)
+    actor = _rand_net([S, 256, 256, 2 * A], ["relu", "relu", "linear"], gen)
+    q1 = _rand_net([S + A, 256, 256, 1], ["relu", "relu", "linear"], gen)
+    q2 = _rand_net([S + A, 256, 256, 1], ["relu", "relu", "linear"], gen)
+    arrays = {}
+    _net_arrays(arrays, "actor0", actor)
+    _net_arrays(arrays, "q1_0", q1)
+    _net_arrays(arrays, "q2_0", q2)
+    b = dict(state=torch.randn(B, S, generator=gen), next_state=torch.randn(B, S, generator=gen),
+             action=torch.rand(B, A, generator=gen) * 1.98 - 0.99,
+             next_action=torch.zeros(B, A), reward=torch.randn(B, 1, generator=gen),
+             not_terminal=(torch.rand(B, 1, generator=gen) > 0.005).float())
+    t = _build_sac(meta, arrays)
+    st = O.SacState(actor, q1, q2, lr=1e-3, entropy_temperature=0.1, learn_alpha=True,
+                    target_entropy=-float(A))
+    gb = _pbatch({k: v.cuda() for k, v in b.items()})
+    for it in range(meta["n_updates"]):
+        nn_, nc = torch.randn(B, A, generator=gen), torch.randn(B, A, generator=gen)
+        arrays[f"noise{it}.next"], arrays[f"noise{it}.cur"] = nn_.numpy(), nc.numpy()
+        _inject(t, arrays, it)
+        out = O.sac_update(st, b, nn_, nc, gamma=0.99, tau=0.005)
+        closs, aloss = t.train_batch(gb, it)
+        assert abs(float(closs[0]) - out["losses"][0]) <= 2e-5 * max(1.0, abs(out["losses"][0]))
+        assert abs(float(closs[1]) - out["losses"][1]) <= 2e-5 * max(1.0, abs(out["losses"][1]))
+        assert abs(float(aloss[0]) - out["losses"][2]) <= 2e-5 * max(1.0, abs(out["losses"][2]))
+        if it == 0:
+            assert G.rel_err(t._ws["td_target"], out["target"].reshape(-1)) < TOL
+    for i, seq in enumerate(t.q1_network.fc.dnn):
+        assert G.rel_err(seq[0].weight, st.q1["W"][i]) < 2e-5
+    for i, seq in enumerate(t.actor_network.fc.dnn):
+        assert G.rel_err(seq[0].weight, st.actor["W"][i]) < 5e-5
+    assert G.rel_err(t.log_alpha, st.log_alpha) < TOL
+
+
+def test_td3_config5_shard_matches_oracle():
+    """BASELINE config 5 per-GPU shard: S=512, A=64, B=2048, [256,256] nets, twin critics."""
+    S, A, B = 512, 64, 2048
+    meta = dict(S=S, A=A, B=B, sizes=[256, 256], acts=["relu", "relu"], twin=True, gamma=0.99,
+                tau=0.005, lr=1e-3, noise_variance=0.2, noise_clip=0.5, delay=2, n_updates=2)
+    gen = torch.Generator().manual_seed(1)
+    actor = _rand_net([S, 256, 256, A], ["relu", "relu", "tanh"], gen)
+    q1 = _rand_net([S + A, 256, 256, 1], ["relu", "relu", "linear"], gen)
+    q2 = _rand_net([S + A, 256, 256, 1], ["relu", "relu", "linear"], gen)
+    arrays = {}
+    _net_arrays(arrays, "actor0", actor)
+    _net_arrays(arrays, "q1_0", q1)
+    _net_arrays(arrays, "q2_0", q2)
+    b = dict(state=torch.randn(B, S, generator=gen), next_state=torch.randn(B, S, generator=gen),
+             action=torch.rand(B, A, generator=gen) * 1.98 - 0.99,
+             next_action=torch.zeros(B, A), reward=torch.randn(B, 1, generator=gen),
+             not_terminal=(torch.rand(B, 1, generator=gen) > 0.005).float())
+    t = _build_td3(meta, arrays)
+    st = O.Td3State(actor, q1, q2, lr=1e-3)
+    gb = _pbatch({k: v.cuda() for k, v in b.items()})
+    for it in range(meta["n_updates"]):
+        nn_ = torch.randn(B, A, generator=gen)
+        arrays[f"noise{it}.next"] = nn_.numpy()
+        _inject(t, arrays, it)
+        out = O.td3_update(st, b, nn_, it, gamma=0.99, tau=0.005)
+        closs, aloss = t.train_batch(gb, it)
+        assert abs(float(closs[0]) - out["losses"][0]) <= TOL * max(1.0, abs(out["losses"][0]))
+        if it == 0:
+            assert G.rel_err(t._ws["td_target"], out["target"].reshape(-1)) < TOL
+    for i, seq in enumerate(t.q1_network.fc.dnn):
+        assert G.rel_err(seq[0].weight, st.q1["W"][i]) < TOL
+    for i, seq in enumerate(t.actor_network.fc.dnn):
+        assert G.rel_err(seq[0].weight, st.actor["W"][i]) < TOL
+    for i, seq in enumerate(t.actor_network_target.fc.dnn):
+        assert G.rel_err(seq[0].weight, st.actor_t["W"][i]) < TOL

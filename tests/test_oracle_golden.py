@@ -84,3 +84,81 @@ def test_replay_oracle_matches_reference(name):
                 keep = ~arrays[f"sample{s_i}.terminal"].reshape(-1)
                 got, want = got[keep], want[keep]
             assert np.array_equal(got, want), key
+
+
+# ---------------------------------------------------------------------------
+# SAC / TD3 restatements vs the reference trainers
+# ---------------------------------------------------------------------------
+SAC_CASES = ["sac_twin_alpha", "sac_single_fixed_alpha", "sac_twin_odd_dims"]
+TD3_CASES = ["td3_twin", "td3_single"]
+
+
+def _cmp_net(net, arrays, prefix, tol):
+    for i in range(len(net["W"])):
+        assert G.rel_err(net["W"][i], arrays[f"{prefix}.W{i}"]) < tol, f"{prefix}.W{i}"
+        assert G.rel_err(net["b"][i], arrays[f"{prefix}.b{i}"]) < tol, f"{prefix}.b{i}"
+
+
+def _cmp_losses(got, want, tol):
+    import numpy as np
+
+    for g, w in zip(got, want):
+        if g is None:
+            assert np.isnan(w)
+        else:
+            assert abs(g - w) <= tol * max(1.0, abs(w)), (got, want)
+
+
+@pytest.mark.parametrize("name", SAC_CASES)
+def test_sac_oracle_matches_reference(name):
+    arrays, meta = G.load(name)
+    acts = meta["acts"] + ["linear"]
+    actor = G.oracle_net(arrays, "actor0", acts)
+    q1 = G.oracle_net(arrays, "q1_0", acts)
+    q2 = G.oracle_net(arrays, "q2_0", acts) if meta["twin"] else None
+    st = O.SacState(actor, q1, q2, lr=meta["lr"], entropy_temperature=meta["entropy_temperature"],
+                    learn_alpha=meta["learn_alpha"], target_entropy=meta["target_entropy"])
+    batch = G.batch_tensors(arrays)
+    for it in range(meta["n_updates"]):
+        out = O.sac_update(st, batch, torch.from_numpy(arrays[f"noise{it}.next"]),
+                           torch.from_numpy(arrays[f"noise{it}.cur"]), gamma=meta["gamma"],
+                           tau=meta["tau"], backprop_through_log_prob=meta["backprop"])
+        _cmp_losses(out["losses"], arrays["losses"][it], 2e-6)
+        if it == 0:
+            names = ["q1"] + (["q2"] if meta["twin"] else []) + ["actor"] + (
+                ["alpha"] if meta["learn_alpha"] else [])
+            for oi, nm in enumerate(names):
+                for pi, g in enumerate(out["grads"][nm]):
+                    assert G.rel_err(g, arrays[f"grad0.opt{oi}.{pi}"]) < 2e-5, (nm, pi)
+    _cmp_net(st.actor, arrays, "actorN", 1e-5)
+    _cmp_net(st.q1, arrays, "q1_N", 1e-5)
+    _cmp_net(st.q1t, arrays, "q1t_N", 1e-5)
+    if meta["twin"]:
+        _cmp_net(st.q2, arrays, "q2_N", 1e-5)
+        _cmp_net(st.q2t, arrays, "q2t_N", 1e-5)
+    if meta["learn_alpha"]:
+        assert G.rel_err(st.log_alpha, arrays["log_alpha_N"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", TD3_CASES)
+def test_td3_oracle_matches_reference(name):
+    arrays, meta = G.load(name)
+    actor = G.oracle_net(arrays, "actor0", meta["acts"] + ["tanh"])
+    cacts = meta["acts"] + ["linear"]
+    q1 = G.oracle_net(arrays, "q1_0", cacts)
+    q2 = G.oracle_net(arrays, "q2_0", cacts) if meta["twin"] else None
+    st = O.Td3State(actor, q1, q2, lr=meta["lr"])
+    batch = G.batch_tensors(arrays)
+    for it in range(meta["n_updates"]):
+        out = O.td3_update(st, batch, torch.from_numpy(arrays[f"noise{it}.next"]), it,
+                           gamma=meta["gamma"], tau=meta["tau"],
+                           noise_variance=meta["noise_variance"], noise_clip=meta["noise_clip"],
+                           delayed_policy_update=meta["delay"])
+        _cmp_losses(out["losses"], arrays["losses"][it], 2e-6)
+    _cmp_net(st.actor, arrays, "actorN", 1e-5)
+    _cmp_net(st.actor_t, arrays, "actort_N", 1e-5)
+    _cmp_net(st.q1, arrays, "q1_N", 1e-5)
+    _cmp_net(st.q1t, arrays, "q1t_N", 1e-5)
+    if meta["twin"]:
+        _cmp_net(st.q2, arrays, "q2_N", 1e-5)
+        _cmp_net(st.q2t, arrays, "q2t_N", 1e-5)
