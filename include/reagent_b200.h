@@ -105,9 +105,11 @@ int rb200_preprocess(const float* input, const void* presence, int32_t presence_
 
 /* Fused whole-MLP forward out = net(cat(in0, in1)) over row tiles; in1 may be NULL.
  * Replaces FullyConnectedNetwork.forward (reagent/models/fully_connected_network.py:157-163)
- * and FullyConnectedCritic.forward's cat (reagent/models/critic.py:76-92). */
+ * and FullyConnectedCritic.forward's cat (reagent/models/critic.py:76-92).  When
+ * save_hidden != NULL the hidden layer outputs go to save_hidden->hidden[l] (training). */
 int rb200_mlp_forward(const rb200_mlp_t* net, const float* in0, int32_t d0, const float* in1,
-                      int32_t d1, int32_t batch, float* out, void* stream);
+                      int32_t d1, int32_t batch, float* out, const rb200_net_ws_t* save_hidden,
+                      void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* K2 (+K2'): fused DQN TD-target / loss / backward over row tiles.            */
@@ -146,6 +148,47 @@ typedef struct rb200_dqn_args {
 int rb200_num_row_tiles(int batch, int max_dim_in, int max_dim_hidden);
 int rb200_dqn_td_step(const rb200_mlp_t* q_net, const rb200_mlp_t* q_target,
                       const rb200_dqn_args_t* args, const rb200_net_ws_t* ws, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* QR-DQN (reagent/training/qrdqn_trainer.py:108-194).  The [hidden -> A*N] head  */
+/* is too wide for a row tile, so it runs as 2-D tiled launches:                   */
+/*   rb200_linear_forward      out = act(in . W^T + b), any N     (nn.Linear fwd) */
+/*   rb200_linear_backward_dx  dz_prev = (dz . W) * act'(h_prev)  (autograd)      */
+/*   rb200_mlp_backward        dZ chain of the layers below a given last-layer dz */
+/*   rb200_qrdqn_head          mean over atoms, masked argmax, target             */
+/*       distribution, pairwise quantile-Huber loss (:152-155, :217-218) and      */
+/*       d loss / d head output, one CTA per row, nothing (N,B,N)-sized in HBM.   */
+/* ------------------------------------------------------------------------- */
+typedef struct rb200_qrdqn_args {
+  int32_t batch, num_actions, num_atoms;
+  const float* q_next_online;  /* [B, A*N] q_network(next_state)  (double-Q) or NULL */
+  const float* q_next_target;  /* [B, A*N] q_network_target(next_state) */
+  const float* q_cur;          /* [B, A*N] q_network(state) */
+  const float* action;         /* [B, A] */
+  const float* next_action;    /* [B, A] (SARSA) or NULL */
+  const float* possible_next_actions_mask; /* [B, A] or NULL */
+  const float* reward;         /* [B] */
+  const float* not_terminal;   /* [B] */
+  const float* discount_src;   /* [B] or NULL: gamma ** discount_src */
+  const float* reward_boost;   /* [A] or NULL */
+  float gamma;
+  int32_t double_q, maxq;
+  float* dz_head;              /* [B, A*N] d loss / d head output */
+  float* all_q_values;         /* [B, A] mean over atoms of q(s), or NULL */
+  int32_t* next_action_idx;    /* [B] or NULL */
+  float* loss_partials;        /* [B] */
+  float* loss;                 /* [1] */
+  uint32_t* tile_counter;      /* [1] zero-initialised, self-resetting */
+} rb200_qrdqn_args_t;
+
+int rb200_linear_forward(const float* W, const float* b, int32_t act, int32_t K, int32_t N,
+                         const float* in, int32_t batch, float* out, void* stream);
+int rb200_linear_backward_dx(const float* W, int32_t K, int32_t N, const float* dz,
+                             const float* h_prev, int32_t act_prev, int32_t batch, float* out,
+                             void* stream);
+int rb200_mlp_backward(const rb200_mlp_t* net, const float* dz_last, int32_t batch,
+                       const rb200_net_ws_t* ws, void* stream);
+int rb200_qrdqn_head(const rb200_qrdqn_args_t* args, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Fused SAC / TD3 updates over row tiles.                                      */

@@ -125,6 +125,73 @@ def dqn_case(name, *, B=48, S=12, A=5, sizes=(24, 20), acts=("relu", "relu"), lo
     _save(name, arrays, meta)
 
 
+def qrdqn_case(name, *, B=32, S=9, A=4, N=7, sizes=(20, 12), acts=("relu", "relu"),
+               double_q=True, maxq=True, multi_steps=None, random_masks=False, gamma=0.97,
+               tau=0.05, lr=1e-2, seed=0):
+    rlt = ref("reagent.core.types")
+    params = ref("reagent.core.parameters")
+    dqn_mod = ref("reagent.models.dqn")
+    tr = ref("reagent.training.qrdqn_trainer")
+    union = ref("reagent.optimizer.union")
+    torch.manual_seed(seed)
+    q = dqn_mod.FullyConnectedDQN(S, A, list(sizes), list(acts), num_atoms=N)
+    with torch.no_grad():
+        for _, b in _fc_params(q):
+            b.normal_(0, 0.1)
+    qt = q.get_target_network()
+    with torch.no_grad():
+        for w, b in _fc_params(qt):
+            w.add_(torch.randn_like(w) * 0.05)
+            b.add_(torch.randn_like(b) * 0.05)
+    rl = params.RLParameters(gamma=gamma, target_update_rate=tau, maxq_learning=maxq,
+                             multi_steps=multi_steps)
+    trainer = tr.QRDQNTrainer(
+        q, qt, actions=[str(i) for i in range(A)], rl=rl, double_q_learning=double_q,
+        num_atoms=N, minibatch_size=B,
+        optimizer=union.Optimizer__Union(Adam=union.classes["Adam"](lr=lr)),
+        evaluation=params.EvaluationParameters(calc_cpe_in_training=False))
+    act_idx = torch.randint(A, (B,))
+    nact_idx = torch.randint(A, (B,))
+    not_terminal = (torch.rand(B, 1) > 0.2).float()
+    pnam = torch.ones(B, A)
+    if random_masks:
+        pnam = (torch.rand(B, A) > 0.3).float()
+        pnam[torch.arange(B), torch.randint(A, (B,))] = 1.0
+    batch = dict(
+        state=torch.randn(B, S), next_state=torch.randn(B, S), reward=torch.randn(B, 1),
+        time_diff=torch.ones(B, 1), step=torch.randint(1, 4, (B, 1)), not_terminal=not_terminal,
+        action=torch.nn.functional.one_hot(act_idx, A).float(),
+        next_action=torch.nn.functional.one_hot(nact_idx, A).float() * not_terminal,
+        possible_actions_mask=torch.ones(B, A), possible_next_actions_mask=pnam)
+    rbatch = rlt.DiscreteDqnInput(
+        state=rlt.FeatureData(batch["state"]), next_state=rlt.FeatureData(batch["next_state"]),
+        reward=batch["reward"], time_diff=batch["time_diff"],
+        step=batch["step"] if multi_steps is not None else None,
+        not_terminal=batch["not_terminal"], action=batch["action"],
+        next_action=batch["next_action"], possible_actions_mask=batch["possible_actions_mask"],
+        possible_next_actions_mask=batch["possible_next_actions_mask"],
+        extras=rlt.ExtraData(action_probability=torch.ones(B, 1)))
+    arrays = {f"batch.{k}": _np(v) for k, v in batch.items()}
+    _dump_net(arrays, "q0", q)
+    _dump_net(arrays, "qt0", qt)
+    opts = [o["optimizer"] for o in trainer.configure_optimizers()]
+    losses = []
+    for it in range(N_UPDATES):
+        cap = {}
+        out = run_update(trainer, rbatch, it, opts, capture=cap)
+        losses.append(out[0])
+        if it == 0:
+            for i, g in enumerate(cap[0]):
+                arrays[f"grad0.{i}"] = _np(g)
+    arrays["losses"] = np.array(losses, dtype=np.float64)
+    _dump_net(arrays, "qN", q)
+    _dump_net(arrays, "qtN", qt)
+    meta = dict(kind="qrdqn", B=B, S=S, A=A, N=N, sizes=list(sizes), acts=list(acts),
+                double_q=double_q, maxq=maxq, multi_steps=multi_steps, gamma=gamma, tau=tau,
+                lr=lr, n_updates=N_UPDATES)
+    _save(name, arrays, meta)
+
+
 # ---------------------------------------------------------------------------
 # replay buffers: the add stream is recorded so the test can replay it
 # ---------------------------------------------------------------------------
@@ -455,6 +522,9 @@ def main():
     sac_case("sac_twin_odd_dims", B=37, S=7, A=2, sizes=(10,), acts=("relu",), seed=5, backprop=False)
     td3_case("td3_twin")
     td3_case("td3_single", twin=False, seed=3, acts=("tanh", "relu"), delay=3)
+    qrdqn_case("qrdqn_double")
+    qrdqn_case("qrdqn_single_masked", double_q=False, random_masks=True, seed=1, N=11)
+    qrdqn_case("qrdqn_sarsa_multistep", maxq=False, multi_steps=3, seed=2, sizes=(16,), acts=("tanh",))
 
 
 if __name__ == "__main__":

@@ -320,3 +320,45 @@ def td3_update(st: Td3State, batch, noise_next, batch_idx, *, gamma, tau, noise_
     else:
         out["losses"].append(None)
     return out
+
+
+# ---------------------------------------------------------------------------
+# QR-DQN (reagent/training/qrdqn_trainer.py:108-194, :210-218)
+# ---------------------------------------------------------------------------
+def qrdqn_loss(q: Net, qt: Net, batch, *, gamma, num_atoms, double_q=True, maxq=True,
+               discount_src=None, reward_boost=None):
+    reward, action = batch["reward"], batch["action"]
+    B, A, N = reward.shape[0], action.shape[1], num_atoms
+    if reward_boost is not None:
+        reward = reward + torch.sum(action.float() * reward_boost, dim=1, keepdim=True)
+    discount = torch.full_like(reward, gamma)
+    if discount_src is not None:
+        discount = torch.pow(gamma, discount_src.float())
+    not_done = batch["not_terminal"].float()
+    quantiles = ((0.5 + torch.arange(N).float()) / float(N)).view(1, -1)  # :70-73
+    next_qf = mlp(qt, batch["next_state"]).view(B, A, N)  # :125
+    if maxq:
+        next_q_values = (mlp(q, batch["next_state"]).view(B, A, N) if double_q else next_qf).mean(dim=2)
+        qv = next_q_values + ACTION_NOT_POSSIBLE_VAL * (1 - batch["possible_next_actions_mask"].float())
+        next_action = qv.argmax(1)  # :210-214
+        next_qf = next_qf[range(B), next_action.reshape(-1)]
+    else:
+        next_action = None
+        next_qf = (next_qf * batch["next_action"].unsqueeze(-1)).sum(1)
+    target_Q = (reward + discount * not_done * next_qf).detach()  # :142
+    current_qf = mlp(q, batch["state"]).view(B, A, N)
+    all_q = current_qf.mean(2).detach()
+    current_qf = (current_qf * action.unsqueeze(-1)).sum(1)  # :149
+    td = target_Q.t().unsqueeze(-1) - current_qf  # (N, B, N), :152
+    huber = torch.where(td.abs() < 1, 0.5 * td.pow(2), td.abs() - 0.5)  # :217-218
+    loss = (huber * (quantiles - (td.detach() < 0).float()).abs()).mean()  # :153-155
+    return loss, {"next_action": next_action, "all_q": all_q, "target": target_Q}
+
+
+def qrdqn_update(q: Net, qt: Net, adam: AdamState, batch, *, gamma, tau, num_atoms, **kw):
+    params = net_params(q)
+    loss, aux = qrdqn_loss(q, qt, batch, gamma=gamma, num_atoms=num_atoms, **kw)
+    grads = [g.detach().clone() for g in torch.autograd.grad(loss, params)]
+    adam.step(params, grads)
+    soft_update(qt, q, tau)
+    return float(loss.detach()), grads, aux

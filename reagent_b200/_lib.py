@@ -145,6 +145,18 @@ class SampleArgsT(C.Structure):
     ]
 
 
+class QrdqnArgsT(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("num_actions", C.c_int32), ("num_atoms", C.c_int32),
+        ("q_next_online", _vp), ("q_next_target", _vp), ("q_cur", _vp), ("action", _vp),
+        ("next_action", _vp), ("possible_next_actions_mask", _vp), ("reward", _vp),
+        ("not_terminal", _vp), ("discount_src", _vp), ("reward_boost", _vp),
+        ("gamma", C.c_float), ("double_q", C.c_int32), ("maxq", C.c_int32),
+        ("dz_head", _vp), ("all_q_values", _vp), ("next_action_idx", _vp),
+        ("loss_partials", _vp), ("loss", _vp), ("tile_counter", _vp),
+    ]
+
+
 class Rb200Error(RuntimeError):
     pass
 
@@ -161,7 +173,13 @@ def _declare(lib):
     lib.rb200_dqn_td_step.argtypes = [C.POINTER(MlpT), C.POINTER(MlpT), C.POINTER(DqnArgsT),
                                       C.POINTER(NetWsT), _vp]
     lib.rb200_mlp_forward.argtypes = [C.POINTER(MlpT), _vp, C.c_int32, _vp, C.c_int32, C.c_int32,
-                                      _vp, _vp]
+                                      _vp, C.POINTER(NetWsT), _vp]
+    lib.rb200_linear_forward.argtypes = [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp,
+                                         C.c_int32, _vp, _vp]
+    lib.rb200_linear_backward_dx.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32,
+                                             C.c_int32, _vp, _vp]
+    lib.rb200_mlp_backward.argtypes = [C.POINTER(MlpT), _vp, C.c_int32, C.POINTER(NetWsT), _vp]
+    lib.rb200_qrdqn_head.argtypes = [C.POINTER(QrdqnArgsT), _vp]
     lib.rb200_preprocess.argtypes = [_vp, _vp, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _vp,
                                      _vp, _vp, _vp]
     lib.rb200_replay_sample.argtypes = [C.POINTER(SampleArgsT), _vp]

@@ -11,6 +11,8 @@ struct FwdDev {
   const float* in1; int d1;   // [B, d1] or nullptr (concatenated after in0)
   float* out;                 // [B, dims[L]]
   int batch, ld_in, ld_h, ld_o;
+  rb200_net_ws_t ws;
+  int save;
 };
 
 template <int NT, int TM, int KC>
@@ -39,7 +41,8 @@ __global__ void __launch_bounds__(NT, 1) mlp_fwd_rows_kernel(const Mlp net, cons
     }
   }
   __syncthreads();
-  tile_mlp_fwd<NT, TM, KC>(net, xin, p.ld_in, hA, hB, p.ld_h, xo, p.ld_o, Wst, nullptr, row0, p.batch);
+  tile_mlp_fwd<NT, TM, KC>(net, xin, p.ld_in, hA, hB, p.ld_h, xo, p.ld_o, Wst,
+                           p.save ? p.ws.hidden : nullptr, row0, p.batch);
   const int DO = net.dims[net.n_layers];
   tile_store_rows<NT, R>(xo, p.ld_o, p.out, DO, DO, row0, p.batch);
 }
@@ -63,7 +66,7 @@ using namespace rb200;
 
 extern "C" int rb200_mlp_forward(const rb200_mlp_t* net, const float* in0, int32_t d0,
                                  const float* in1, int32_t d1, int32_t batch, float* out,
-                                 void* stream) {
+                                 const rb200_net_ws_t* save_hidden, void* stream) {
   if (!net || !in0 || !out) { set_last_error("rb200_mlp_forward: null argument"); return RB200_E_INVALID; }
   if (int rc = validate_mlp(net, "net")) return rc;
   if (batch <= 0) { set_last_error("rb200_mlp_forward: batch must be positive"); return RB200_E_INVALID; }
@@ -73,6 +76,8 @@ extern "C" int rb200_mlp_forward(const rb200_mlp_t* net, const float* in0, int32
   }
   FwdDev p;
   p.in0 = in0; p.d0 = d0; p.in1 = in1; p.d1 = in1 ? d1 : 0; p.out = out; p.batch = batch;
+  p.save = save_hidden ? 1 : 0;
+  if (save_hidden) p.ws = *save_hidden; else p.ws = rb200_net_ws_t{};
   const int DO = net->dims[net->n_layers];
   const int hmax = mlp_max_hidden(net);
   p.ld_o = round_up4(DO) + 4;

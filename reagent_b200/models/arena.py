@@ -51,14 +51,16 @@ class ParamArena:
         o = self.dims[l + 1]
         return flat[self.b_off[l]: self.b_off[l] + o]
 
-    def desc(self) -> _lib.MlpT:
-        """ctypes descriptor for the current flat buffer."""
+    def desc(self, n_layers=None) -> _lib.MlpT:
+        """ctypes descriptor for the current flat buffer (optionally only the first
+        `n_layers` layers, e.g. the trunk below a wide head)."""
         assert self.flat is not None
+        L = len(self.acts) if n_layers is None else n_layers
         d = _lib.MlpT()
-        d.n_layers = len(self.acts)
-        for i, v in enumerate(self.dims):
+        d.n_layers = L
+        for i, v in enumerate(self.dims[: L + 1]):
             d.dims[i] = v
-        for i, a in enumerate(self.acts):
+        for i, a in enumerate(self.acts[:L]):
             d.act[i] = a
             d.w_off[i] = self.w_off[i]
             d.b_off[i] = self.b_off[i]

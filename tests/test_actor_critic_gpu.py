@@ -227,16 +227,30 @@ def test_sac_config4_shard_matches_oracle():
         arrays[f"noise{it}.next"], arrays[f"noise{it}.cur"] = nn_.numpy(), nc.numpy()
         _inject(t, arrays, it)
         out = O.sac_update(st, b, nn_, nc, gamma=0.99, tau=0.005)
+        if it == 0:
+            # gradients straight out of the fused backward (before Adam touches them)
+            t._critic_step(gb, t.actor_network, t.q1_network_target, t.q2_network_target,
+                           t._fill_critic)
+            for pi, g in enumerate(t.net_grads(t.q1_network)):
+                assert G.rel_err(g, out["grads"]["q1"][pi]) < TOL, ("q1 grad", pi)
+            for pi, g in enumerate(t.net_grads(t.q2_network)):
+                assert G.rel_err(g, out["grads"]["q2"][pi]) < TOL, ("q2 grad", pi)
         closs, aloss = t.train_batch(gb, it)
         assert abs(float(closs[0]) - out["losses"][0]) <= 2e-5 * max(1.0, abs(out["losses"][0]))
         assert abs(float(closs[1]) - out["losses"][1]) <= 2e-5 * max(1.0, abs(out["losses"][1]))
         assert abs(float(aloss[0]) - out["losses"][2]) <= 2e-5 * max(1.0, abs(out["losses"][2]))
         if it == 0:
             assert G.rel_err(t._ws["td_target"], out["target"].reshape(-1)) < TOL
+    # Post-Adam weights: the first Adam steps move every element by ~lr*g/(|g|+eps), so an
+    # element whose gradient is within fp32 noise of zero moves by up to ~lr regardless of
+    # how well the gradients agree (they agree to 1e-5 above).  Bound the deviation by a
+    # fraction of the step size instead of 1e-5 of the weight scale.
     for i, seq in enumerate(t.q1_network.fc.dnn):
-        assert G.rel_err(seq[0].weight, st.q1["W"][i]) < 2e-5
+        d = (seq[0].weight.detach().cpu() - st.q1["W"][i].detach()).abs().max()
+        assert float(d) < 0.05 * meta["n_updates"] * meta["lr"], (i, float(d))
     for i, seq in enumerate(t.actor_network.fc.dnn):
-        assert G.rel_err(seq[0].weight, st.actor["W"][i]) < 5e-5
+        d = (seq[0].weight.detach().cpu() - st.actor["W"][i].detach()).abs().max()
+        assert float(d) < 0.05 * meta["n_updates"] * meta["lr"], (i, float(d))
     assert G.rel_err(t.log_alpha, st.log_alpha) < TOL
 
 
@@ -265,13 +279,18 @@ def test_td3_config5_shard_matches_oracle():
         arrays[f"noise{it}.next"] = nn_.numpy()
         _inject(t, arrays, it)
         out = O.td3_update(st, b, nn_, it, gamma=0.99, tau=0.005)
+        if it == 0:
+            t._critic_step(gb, t.actor_network_target, t.q1_network_target,
+                           t.q2_network_target, t._fill)
+            for pi, g in enumerate(t.net_grads(t.q1_network)):
+                assert G.rel_err(g, out["grads"]["q1"][pi]) < TOL, ("q1 grad", pi)
         closs, aloss = t.train_batch(gb, it)
         assert abs(float(closs[0]) - out["losses"][0]) <= TOL * max(1.0, abs(out["losses"][0]))
         if it == 0:
             assert G.rel_err(t._ws["td_target"], out["target"].reshape(-1)) < TOL
-    for i, seq in enumerate(t.q1_network.fc.dnn):
-        assert G.rel_err(seq[0].weight, st.q1["W"][i]) < TOL
-    for i, seq in enumerate(t.actor_network.fc.dnn):
-        assert G.rel_err(seq[0].weight, st.actor["W"][i]) < TOL
+    for net, onet in ((t.q1_network, st.q1), (t.actor_network, st.actor)):
+        for i, seq in enumerate(net.fc.dnn):
+            d = (seq[0].weight.detach().cpu() - onet["W"][i].detach()).abs().max()
+            assert float(d) < 0.05 * meta["n_updates"] * meta["lr"], (i, float(d))
     for i, seq in enumerate(t.actor_network_target.fc.dnn):
         assert G.rel_err(seq[0].weight, st.actor_t["W"][i]) < TOL

@@ -162,3 +162,28 @@ def test_td3_oracle_matches_reference(name):
     if meta["twin"]:
         _cmp_net(st.q2, arrays, "q2_N", 1e-5)
         _cmp_net(st.q2t, arrays, "q2t_N", 1e-5)
+
+
+QRDQN_CASES = ["qrdqn_double", "qrdqn_single_masked", "qrdqn_sarsa_multistep"]
+
+
+@pytest.mark.parametrize("name", QRDQN_CASES)
+def test_qrdqn_oracle_matches_reference(name):
+    arrays, meta = G.load(name)
+    acts = meta["acts"] + ["linear"]
+    q = G.oracle_net(arrays, "q0", acts, requires_grad=True)
+    qt = G.oracle_net(arrays, "qt0", acts)
+    batch = G.batch_tensors(arrays)
+    adam = O.AdamState(O.net_params(q), lr=meta["lr"])
+    kw = dict(double_q=meta["double_q"], maxq=meta["maxq"], num_atoms=meta["N"])
+    if meta["multi_steps"] is not None:
+        kw["discount_src"] = batch["step"]
+    for it in range(meta["n_updates"]):
+        loss, grads, aux = O.qrdqn_update(q, qt, adam, batch, gamma=meta["gamma"], tau=meta["tau"], **kw)
+        assert abs(loss - arrays["losses"][it]) <= 1e-6 * max(1.0, abs(arrays["losses"][it]))
+        if it == 0:
+            for i, g in enumerate(grads):
+                assert G.rel_err(g, arrays[f"grad0.{i}"]) < 1e-6
+    for i in range(len(q["W"])):
+        assert G.rel_err(q["W"][i], arrays[f"qN.W{i}"]) < 1e-6
+        assert G.rel_err(qt["W"][i], arrays[f"qtN.W{i}"]) < 1e-6
