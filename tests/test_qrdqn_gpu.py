@@ -99,6 +99,7 @@ def test_qrdqn_config3_shape_matches_oracle():
              possible_actions_mask=torch.ones(B, A), possible_next_actions_mask=torch.ones(B, A))
     t = _build(meta, arrays)
     qo = O.clone_net(q, requires_grad=True)
+    qt_before = O.clone_net(qt)
     adam = O.AdamState(O.net_params(qo), lr=1e-3)
     lo, grads, aux = O.qrdqn_update(qo, qt, adam, b, gamma=0.99, tau=0.005, num_atoms=N)
     gb = _batch({k: (v.cuda() if v is not None else None) for k, v in b.items()}, meta)
@@ -112,4 +113,4 @@ def test_qrdqn_config3_shape_matches_oracle():
     from reagent_b200.core import types as rlt
     out = t.q_network_target(rlt.FeatureData(gb.state.float_features))
     assert out.shape == (B, A, N)
-    assert G.rel_err(out.reshape(B, -1), O.mlp(qt, b["state"])) < TOL
+    assert G.rel_err(out.reshape(B, -1), O.mlp(qt_before, b["state"])) < TOL
