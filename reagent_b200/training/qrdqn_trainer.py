@@ -200,14 +200,13 @@ class QRDQNTrainer(DQNTrainerBaseLightning):
         if process_group is None:
             opts[0].fused_step(target=self.q_network_target.arena, tau=self.tau)
         else:
-            import torch.distributed as dist
-
+            from .data_parallel import allreduce_mean_
             from .workspace import reduced_grad
 
             g = reduced_grad(self.q_network.arena)
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=process_group)
+            scale = allreduce_mean_(g, process_group)
             opts[0].fused_step(target=self.q_network_target.arena, tau=self.tau, grad=g,
-                               grad_scale=1.0 / dist.get_world_size(process_group))
+                               grad_scale=scale)
         self.all_batches_processed += 1
         return self._ws["loss"]
 

@@ -190,11 +190,10 @@ class SACTrainer(ActorCriticBase):
         if process_group is None:
             opt.fused_step(target=target, tau=self.tau, exp_out=exp_out)
             return
-        import torch.distributed as dist
-
+        from .data_parallel import allreduce_mean_
         from .workspace import reduced_grad
 
         g = reduced_grad(arena)
-        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=process_group)
+        scale = allreduce_mean_(g, process_group)
         opt.fused_step(target=target, tau=self.tau, grad=g, exp_out=exp_out,
-                       grad_scale=1.0 / dist.get_world_size(process_group))
+                       grad_scale=scale)
