@@ -59,6 +59,7 @@ ac_critic_rows_kernel(const Mlp actor, const Mlp q1, const Mlp q2, const Mlp q1t
   const rb200_ac_args_t& a = p.a;
   const int tid = threadIdx.x;
   const int ld_c = p.ld_c, ld_h = p.ld_h, ld_o = p.ld_o;
+  tile_smem_zero_all<NT>(smem);
   float* Wst = smem;
   float* cin = Wst + 2 * wstage_floats<KC>();  // [R, ld_c] critic input cat(state, action)
   float* hA = cin + R * ld_c;
@@ -199,6 +200,7 @@ ac_actor_rows_kernel(const Mlp actor, const Mlp q1, const Mlp q2, const AcDev p)
   const rb200_ac_args_t& a = p.a;
   const int tid = threadIdx.x;
   const int ld_c = p.ld_c, ld_h = p.ld_h, ld_o = p.ld_o;
+  tile_smem_zero_all<NT>(smem);
   float* Wst = smem;
   float* cin = Wst + 2 * wstage_floats<KC>();
   float* hA = cin + R * ld_c;

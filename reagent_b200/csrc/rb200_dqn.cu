@@ -29,6 +29,7 @@ dqn_td_rows_kernel(const Mlp q, const Mlp qt, const DqnDev p) {
   const rb200_dqn_args_t& a = p.a;
   const int tid = threadIdx.x;
   const int ld_in = p.ld_in, ld_h = p.ld_h, ld_q = p.ld_q;
+  tile_smem_zero_all<NT>(smem);
   float* Wst = smem;
   float* xin = Wst + 2 * wstage_floats<KC>();
   float* hA = xin + R * ld_in;

@@ -19,6 +19,7 @@ template <int NT, int TM, int KC>
 __global__ void __launch_bounds__(NT, 1) mlp_fwd_rows_kernel(const Mlp net, const FwdDev p) {
   constexpr int R = (NT / 64) * TM;
   extern __shared__ __align__(16) float smem[];
+  tile_smem_zero_all<NT>(smem);
   float* Wst = smem;
   float* xin = Wst + 2 * wstage_floats<KC>();
   float* hA = xin + R * p.ld_in;

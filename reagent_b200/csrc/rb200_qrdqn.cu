@@ -25,6 +25,7 @@ template <int NT, int TM, int KC>
 __global__ void __launch_bounds__(NT, 1) linear_fwd_wide_kernel(const LinFwdDev p) {
   constexpr int R = (NT / 64) * TM;
   extern __shared__ __align__(16) float smem[];
+  tile_smem_zero_all<NT>(smem);
   float* Wst = smem;
   float* xin = Wst + 2 * wstage_floats<KC>();
   float* xo = xin + R * p.ld_in;
@@ -51,6 +52,7 @@ template <int NT, int TM, int KC>
 __global__ void __launch_bounds__(NT, 1) linear_bwd_wide_kernel(const LinBwdDev p) {
   constexpr int R = (NT / 64) * TM;
   extern __shared__ __align__(16) float smem[];
+  tile_smem_zero_all<NT>(smem);
   float* Wst = smem;
   float* zs = Wst + 2 * wstage_floats<KC>();  // [R, ld_z] slab of dz
   float* accb = zs + R * p.ld_z;              // [R, ld_k] running sum
@@ -93,6 +95,7 @@ template <int NT, int TM, int KC>
 __global__ void __launch_bounds__(NT, 1) mlp_bwd_rows_kernel(const Mlp net, const MlpBwdDev p) {
   constexpr int R = (NT / 64) * TM;
   extern __shared__ __align__(16) float smem[];
+  tile_smem_zero_all<NT>(smem);
   float* Wst = smem;
   float* gA = Wst + 2 * wstage_floats<KC>();
   float* gB = gA + R * p.ld_h;

@@ -1,5 +1,8 @@
 // reagent_b200 -- host-side tile configuration shared by the row-tile kernels.
 #pragma once
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "rb200_tile.cuh"
 
 namespace rb200 {
@@ -26,10 +29,14 @@ inline RowsCfg pick_rows_cfg(int batch, int din, int hmax, int n_in, int n_h, in
   // (threads, rows/thread, k-chunk): 16 warps per SM hide the LDS->FMA latency of the
   // 4x4 register tile; the 16-row tile serves small batches (more CTAs than SMs).
   const int cand[4][3] = {{512, 4, 32}, {512, 4, 16}, {256, 4, 32}, {256, 4, 16}};
+  const char* force = getenv("RB200_FORCE_CFG");  // tuning / profiling only: "nt,kc"
+  int fnt = 0, fkc = 0;
+  if (force) sscanf(force, "%d,%d", &fnt, &fkc);
   for (int c = 0; c < 4; ++c) {
     const int nt = cand[c][0], tm = cand[c][1], kc = cand[c][2];
     const int R = (nt / 64) * tm;
-    if (R == 32 && batch <= 16 * 148) continue;  // small batch: prefer 16-row tiles
+    if (fnt) { if (nt != fnt || kc != fkc) continue; }
+    else if (R == 32 && batch <= 16 * 148) continue;  // small batch: prefer 16-row tiles
     const size_t stage = (size_t)(kc == 32 ? wstage_floats<32>() : wstage_floats<16>());
     const size_t floats = 2 * stage + (size_t)R * ((size_t)n_in * ld_in + (size_t)n_h * ld_h +
                                                    (size_t)extra_per_row) + (size_t)extra;

@@ -1,4 +1,4 @@
-// reagent_b200 -- row-tile MLP primitives (fp32 CUDA-core path).
+// reagent_b200 -- row-tile MLP primitives (tensor cores: mma.sync TF32 with 3xTF32 split).
 //
 // A CTA of NT (256 or 512) threads owns a tile of R = (NT/64)*TM batch rows and walks whole MLPs
 // over it with every activation resident in shared memory; only weights stream
@@ -7,8 +7,7 @@
 //   tile_linear_fwd : C[R,N]  = act(A[R,K] . W[N,K]^T + b)        (nn.Linear forward)
 //   tile_linear_bwd : dA[R,K] = dZ[R,N] . W[N,K]                  (input gradient)
 //
-// Thread mapping: 2-D warp tiling, see "Warp tiling" below (every LDS.128 is a single
-// shared-memory wavefront, 8 wavefronts per 64 FMA instructions per warp).
+// The inner products run on the tensor cores (see "Tensor-core inner product" below).
 #pragma once
 #include "rb200_common.cuh"
 
@@ -18,154 +17,57 @@ constexpr int kNC = 256;  // output-column chunk processed per pass
 
 template <int KC>
 __host__ __device__ constexpr int wstage_floats() {
-  // one stage must hold either the fwd chunk [256][KC+4] or the bwd chunk [KC][256+4]
-  return (kNC * (KC + 4) > KC * (kNC + 4)) ? kNC * (KC + 4) : KC * (kNC + 4);
+  // one stage must hold either the fwd chunk [256][KC+4] or the bwd chunk [KC][256+8]
+  return (kNC * (KC + 4) > KC * (kNC + 8)) ? kNC * (KC + 4) : KC * (kNC + 8);
 }
 
 // ---------------------------------------------------------------------------
-// Warp tiling.  The NW = NT/32 warps of the CTA are arranged WR x WC over the
-// (R rows) x (256-column chunk) output; a warp owns a (4*TMe rows) x 32 columns block and
-// its lanes are laid out 4 (row lanes, lr) x 8 (column lanes, lc):
-//   thread rows  r = warp_row0 + lr + 4*i        (i < TMe)
-//   thread cols  fwd: c = warp_col0 + lc + 8*j   (j < 4)      bwd: c = warp_col0 + 4*lc + (0..3)
-// Per 4-deep k step a warp touches only 4*TMe row quads + 32 column quads of shared memory:
-// every LDS.128 is ONE wavefront (column lanes read 8 distinct 16-byte quads that the 4 row
-// lanes share by broadcast, and vice versa; the +4 float row padding keeps the quads of
-// different rows in different banks).  8 wavefronts per 64 FMA-instructions per warp keeps
-// the loop FMA-pipe bound (a 1-D lane mapping needs 20 and is shared-memory bound).
-// WC adapts to the chunk width (8 / 4 / 2 column warps) so narrow layers waste no FMAs.
+// Tensor-core inner product: mma.sync.m16n8k8 TF32 with 3xTF32 error compensation.
+//   x = hi + lo (hi = rna_tf32(x), lo = rna_tf32(x - hi));  a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
+// fp32 accumulation in the MMA; the dropped a_lo*b_lo term is ~2^-22 relative, which keeps the
+// 1e-5 parity bar of the north star (plain TF32 would be ~1e-3).  Measured on this B200 pool
+// (profiles/micro/pipes.cu): FFMA 56 TFLOP/s, mma.sync TF32 277 TFLOP/s -> 92 TFLOP/s
+// algorithmic for 3xTF32 with ~10x fewer issue slots than the FFMA loop.
+// Fragment <-> shared-memory mapping (g = lane/4, t = lane%4), all LDS.32 conflict-free:
+//   A (16x8, row-major tile of the activations, stride == 4 mod 32): a0 (g,t) a1 (g+8,t)
+//                                                                   a2 (g,t+4) a3 (g+8,t+4)
+//   B fwd (W chunk staged [n][KC+4], stride == 4 mod 32):  b0 = Ws[n0+g][k+t], b1 = Ws[n0+g][k+t+4]
+//   B bwd (W chunk staged [n][256+8], stride == 8 mod 32): b0 = Ws[n+t][c0+g], b1 = Ws[n+t+4][c0+g]
+//   C: c0 (g,2t) c1 (g,2t+1) c2 (g+8,2t) c3 (g+8,2t+1)
+// A warp owns ALL row tiles (R/16) and the 8-column tiles  warp, warp+NW, ...  of the chunk, so
+// narrow layers still spread over every warp.
 // ---------------------------------------------------------------------------
-// Fragments are double buffered in registers: the LDS.128 of step s+1 are issued before the
-// FMAs of step s, so the ~30-cycle shared-memory latency is covered by 16*TMe FMAs of the
-// same warp (ptxas otherwise schedules each load right before its first use).
-template <int TMe>
-struct FragF {
-  float4 w[4];
-  float4 a[TMe];
-};
-
-template <int TMe>
-__device__ __forceinline__ void fwd_load(FragF<TMe>& f, const float* __restrict__ arow, int lda4,
-                                         const float* __restrict__ wrow, int lw8, int kk) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) f.w[j] = *reinterpret_cast<const float4*>(wrow + j * lw8 + kk);
-#pragma unroll
-  for (int i = 0; i < TMe; ++i) f.a[i] = *reinterpret_cast<const float4*>(arow + i * lda4 + kk);
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
 }
 
-template <int TMe>
-__device__ __forceinline__ void fwd_fma(float (&acc)[4][4], const FragF<TMe>& f) {
-  // k-outer order: 4*TMe independent FMAs between two uses of the same accumulator
-#pragma unroll
-  for (int i = 0; i < TMe; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(f.a[i].x, f.w[j].x, acc[i][j]);
-#pragma unroll
-  for (int i = 0; i < TMe; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(f.a[i].y, f.w[j].y, acc[i][j]);
-#pragma unroll
-  for (int i = 0; i < TMe; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(f.a[i].z, f.w[j].z, acc[i][j]);
-#pragma unroll
-  for (int i = 0; i < TMe; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(f.a[i].w, f.w[j].w, acc[i][j]);
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4],
+                                         const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+      "{%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-template <int TMe>
-__device__ __forceinline__ void fwd_inner(float (&acc)[4][4], const float* __restrict__ arow,
-                                          int lda4, const float* __restrict__ wrow, int lw8,
-                                          int klen) {
-  const int steps = klen >> 2;
-  FragF<TMe> f0, f1;
-  fwd_load<TMe>(f0, arow, lda4, wrow, lw8, 0);
-  int s = 0;
-#pragma unroll 1
-  for (; s + 1 < steps; s += 2) {
-    fwd_load<TMe>(f1, arow, lda4, wrow, lw8, (s + 1) * 4);
-    fwd_fma<TMe>(acc, f0);
-    if (s + 2 < steps) fwd_load<TMe>(f0, arow, lda4, wrow, lw8, (s + 2) * 4);
-    fwd_fma<TMe>(acc, f1);
-  }
-  if (s < steps) fwd_fma<TMe>(acc, f0);
+__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4],
+                                           const uint32_t (&al)[4], const uint32_t (&bh)[2],
+                                           const uint32_t (&bl)[2]) {
+  mma_tf32(c, al, bh);
+  mma_tf32(c, ah, bl);
+  mma_tf32(c, ah, bh);
 }
 
-template <int TMe>
-struct FragB {
-  float4 w[4];
-  float4 z[TMe];
-};
-
-template <int TMe>
-__device__ __forceinline__ void bwd_load(FragB<TMe>& f, const float* __restrict__ zrow, int ldz4,
-                                         const float* __restrict__ wcol, int LW, int nn) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) f.w[j] = *reinterpret_cast<const float4*>(wcol + (nn + j) * LW);
-#pragma unroll
-  for (int i = 0; i < TMe; ++i) f.z[i] = *reinterpret_cast<const float4*>(zrow + i * ldz4 + nn);
-}
-
-template <int TMe>
-__device__ __forceinline__ void bwd_fma(float (&acc)[4][4], const FragB<TMe>& f) {
-#pragma unroll
-  for (int i = 0; i < TMe; ++i) {
-    acc[i][0] = fmaf(f.z[i].x, f.w[0].x, acc[i][0]);
-    acc[i][1] = fmaf(f.z[i].x, f.w[0].y, acc[i][1]);
-    acc[i][2] = fmaf(f.z[i].x, f.w[0].z, acc[i][2]);
-    acc[i][3] = fmaf(f.z[i].x, f.w[0].w, acc[i][3]);
-  }
-#pragma unroll
-  for (int i = 0; i < TMe; ++i) {
-    acc[i][0] = fmaf(f.z[i].y, f.w[1].x, acc[i][0]);
-    acc[i][1] = fmaf(f.z[i].y, f.w[1].y, acc[i][1]);
-    acc[i][2] = fmaf(f.z[i].y, f.w[1].z, acc[i][2]);
-    acc[i][3] = fmaf(f.z[i].y, f.w[1].w, acc[i][3]);
-  }
-#pragma unroll
-  for (int i = 0; i < TMe; ++i) {
-    acc[i][0] = fmaf(f.z[i].z, f.w[2].x, acc[i][0]);
-    acc[i][1] = fmaf(f.z[i].z, f.w[2].y, acc[i][1]);
-    acc[i][2] = fmaf(f.z[i].z, f.w[2].z, acc[i][2]);
-    acc[i][3] = fmaf(f.z[i].z, f.w[2].w, acc[i][3]);
-  }
-#pragma unroll
-  for (int i = 0; i < TMe; ++i) {
-    acc[i][0] = fmaf(f.z[i].w, f.w[3].x, acc[i][0]);
-    acc[i][1] = fmaf(f.z[i].w, f.w[3].y, acc[i][1]);
-    acc[i][2] = fmaf(f.z[i].w, f.w[3].z, acc[i][2]);
-    acc[i][3] = fmaf(f.z[i].w, f.w[3].w, acc[i][3]);
-  }
-}
-
-template <int TMe>
-__device__ __forceinline__ void bwd_inner(float (&acc)[4][4], const float* __restrict__ zrow,
-                                          int ldz4, const float* __restrict__ wcol, int LW,
-                                          int nlen) {
-  const int steps = nlen >> 2;
-  FragB<TMe> f0, f1;
-  bwd_load<TMe>(f0, zrow, ldz4, wcol, LW, 0);
-  int s = 0;
-#pragma unroll 1
-  for (; s + 1 < steps; s += 2) {
-    bwd_load<TMe>(f1, zrow, ldz4, wcol, LW, (s + 1) * 4);
-    bwd_fma<TMe>(acc, f0);
-    if (s + 2 < steps) bwd_load<TMe>(f0, zrow, ldz4, wcol, LW, (s + 2) * 4);
-    bwd_fma<TMe>(acc, f1);
-  }
-  if (s < steps) bwd_fma<TMe>(acc, f0);
-}
-
-// column-warp count for a chunk that is `cols` wide
-__device__ __forceinline__ int pick_wc(int cols) { return cols > 128 ? 8 : (cols > 64 ? 4 : 2); }
+constexpr int kLWB = kNC + 8;  // bwd staging row stride (== 8 mod 32)
 
 // ---------------------------------------------------------------------------
 // forward:  Cs[r, 0..N) = act(As[r, 0..K) . Wg[n, 0..K) + bg[n])
-//   As : smem, row stride lda (multiple of 4), columns K..round_up4(K)-1 MUST be 0
+//   As : smem, row stride lda (== 4 mod 32), finite everywhere, 0 in columns K..round_up4(K)-1
 //   Cs : smem, row stride ldc (multiple of 4); columns N..round_up4(N)-1 are zeroed
 //   Wst: smem staging, 2 * wstage_floats<KC>() floats, 16B aligned; W chunk staged as
-//        Ws[256][KC+4] (K contiguous)
+//        Ws[256][KC+4] (K contiguous), k >= K zero filled
 // All NT threads must call (contains __syncthreads).
 // ---------------------------------------------------------------------------
 template <int NT, int TM, int KC>
@@ -179,18 +81,23 @@ __device__ __noinline__ void tile_linear_fwd(const float* __restrict__ As, int l
   constexpr int QPR = KC / 4;  // 16B quads per staged row
   constexpr int NW = NT / 32;
   constexpr int R = (NT / 64) * TM;
-  static_assert(TM == 4, "warp tiling assumes 4 rows per thread at full chunk width");
+  constexpr int MT = R / 16;          // 16-row MMA tiles
+  constexpr int NTW = (kNC / 8) / NW; // 8-column tiles per warp at full chunk width
+  static_assert(R % 16 == 0, "row tile must be a multiple of the MMA M");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int lr = lane >> 3, lc = lane & 7;
+  const int g = lane >> 2, t = lane & 3;
   const int nk = ceil_div(K, KC), nn = ceil_div(N, kNC), total = nk * nn;
   const bool vec = ((ldw & 3) == 0) && ((reinterpret_cast<uintptr_t>(Wg) & 15) == 0);
+  // every CTA walks the k-chunks in a different rotation: all CTAs stream the SAME weights,
+  // and in lock-step they would hammer the same L2 lines at the same time
+  const int rot = blockIdx.x % nk;
 
   // staging map: thread -> (quad lq of the k-chunk, rows lr0, lr0+RPI, ...): fixed per thread
   constexpr int RPI = NT / QPR;
   const int lq = tid % QPR, lr0 = tid / QPR;
   auto load_chunk = [&](int c, int stage) {
     const int nci = c / nk, kci = c - nci * nk;
-    const int n0 = nci * kNC, k0 = kci * KC;
+    const int n0 = nci * kNC, k0 = ((kci + rot) % nk) * KC;
     float* dst = Wst + stage * STAGE;
     const int rows = min(kNC, N - n0);
     const int k = k0 + 4 * lq;
@@ -215,23 +122,21 @@ __device__ __noinline__ void tile_linear_fwd(const float* __restrict__ As, int l
     }
   };
 
-  float acc[4][4];
+  float acc[MT][NTW][4];
   load_chunk(0, 0);
   cp_async_commit();
   for (int c = 0; c < total; ++c) {
     const int nci = c / nk, kci = c - nci * nk;
-    const int n0 = nci * kNC, k0 = kci * KC;
+    const int n0 = nci * kNC, k0 = ((kci + rot) % nk) * KC;
     const int ncols = min(kNC, N - n0);
-    const int WC = pick_wc(ncols), WR = NW / WC;
-    const int wr = warp / WC, wc = warp - wr * WC;
-    const int rpw = R / WR;              // rows per warp = 4 * TMe
-    const int row0 = wr * rpw + lr;      // thread rows row0 + 4*i
-    const int col0 = wc * 32 + lc;       // thread cols (chunk relative) col0 + 8*j
+    const int ntiles = ceil_div(ncols, 8);
     if (kci == 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int m = 0; m < MT; ++m)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < NTW; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.f;
     }
     if (c + 1 < total) {
       load_chunk(c + 1, (c + 1) & 1);
@@ -242,27 +147,52 @@ __device__ __noinline__ void tile_linear_fwd(const float* __restrict__ As, int l
     }
     __syncthreads();
     const float* Ws = Wst + (c & 1) * STAGE;
-    if (wc * 32 < ncols) {
-      const int klen = min(KC, round_up4(K - k0));
-      const float* arow = As + row0 * lda + k0;
-      const float* wrow = Ws + col0 * LW;
-      if (rpw == 16) fwd_inner<4>(acc, arow, 4 * lda, wrow, 8 * LW, klen);
-      else if (rpw == 8) fwd_inner<2>(acc, arow, 4 * lda, wrow, 8 * LW, klen);
-      else fwd_inner<1>(acc, arow, 4 * lda, wrow, 8 * LW, klen);
+    if (warp < ntiles) {
+      const int klen = min(KC, (K - k0 + 7) & ~7);
+      const float* ab = As + g * lda + k0 + t;
+      for (int kk = 0; kk < klen; kk += 8) {
+        uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const float* ap = ab + m * 16 * lda + kk;
+          split_tf32(ap[0], ah[m][0], al[m][0]);
+          split_tf32(ap[8 * lda], ah[m][1], al[m][1]);
+          split_tf32(ap[4], ah[m][2], al[m][2]);
+          split_tf32(ap[8 * lda + 4], ah[m][3], al[m][3]);
+        }
+#pragma unroll
+        for (int j = 0; j < NTW; ++j) {
+          const int nt = warp + j * NW;
+          if (nt < ntiles) {
+            const float* bp = Ws + (nt * 8 + g) * LW + kk + t;
+            uint32_t bh[2], bl[2];
+            split_tf32(bp[0], bh[0], bl[0]);
+            split_tf32(bp[4], bh[1], bl[1]);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) mma_3xtf32(acc[m][j], ah[m], al[m], bh, bl);
+          }
+        }
+      }
     }
-    if (kci == nk - 1 && wc * 32 < round_up4(ncols)) {
+    if (kci == nk - 1) {
       const int n4 = round_up4(N);
-      const int tme = rpw >> 2;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int col = n0 + col0 + 8 * j;
-        if (col < n4) {
-          const bool real = col < N;
-          const float b = (real && bg != nullptr) ? bg[col] : 0.f;
+      for (int j = 0; j < NTW; ++j) {
+        const int nt = warp + j * NW;
+        if (nt < ntiles) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < tme)
-              Cs[(row0 + 4 * i) * ldc + col] = real ? act_fwd(acc[i][j] + b, act) : 0.f;
+          for (int e = 0; e < 2; ++e) {
+            const int col = n0 + nt * 8 + 2 * t + e;
+            if (col < n4) {
+              const bool real = col < N;
+              const float b = (real && bg != nullptr) ? bg[col] : 0.f;
+#pragma unroll
+              for (int m = 0; m < MT; ++m) {
+                Cs[(m * 16 + g) * ldc + col] = real ? act_fwd(acc[m][j][e] + b, act) : 0.f;
+                Cs[(m * 16 + g + 8) * ldc + col] = real ? act_fwd(acc[m][j][2 + e] + b, act) : 0.f;
+              }
+            }
+          }
         }
       }
     }
@@ -274,10 +204,10 @@ __device__ __noinline__ void tile_linear_fwd(const float* __restrict__ As, int l
 // backward (input gradient):  dAs[r, 0..Kout) = dZs[r, 0..N) . Wg[n, kcol0 .. kcol0+Kout)
 //   then, if Hs != nullptr, multiplied elementwise by act'(Hs[r,k]) (Hs = the
 //   activation OUTPUT that produced this input, same column indexing as dAs).
-//   dZs: smem, stride ldz, columns N..round_up4(N)-1 MUST be 0.
+//   dZs: smem, stride ldz (== 4 mod 32), finite everywhere, 0 in columns N..round_up4(N)-1.
 //   dAs: smem, stride lda; columns Kout..round_up4(Kout)-1 are zeroed.
 //   Wg points at W[0][kcol0]; ldw is the full row stride of W.  W chunk staged as
-//   Ws[KC][256+4] (rows = contraction index n).
+//   Ws[KC][256+8] (rows = contraction index n, zero filled for n >= N).
 // ---------------------------------------------------------------------------
 template <int NT, int TM, int KC>
 __device__ __noinline__ void tile_linear_bwd(const float* __restrict__ dZs, int ldz, int N,
@@ -285,15 +215,18 @@ __device__ __noinline__ void tile_linear_bwd(const float* __restrict__ dZs, int 
                                              const float* __restrict__ Hs, int ldh, int hact,
                                              float* __restrict__ dAs, int lda,
                                              float* __restrict__ Wst) {
-  constexpr int LW = kNC + 4;
+  constexpr int LW = kLWB;
   constexpr int STAGE = wstage_floats<KC>();
   constexpr int NR = KC;  // contraction rows per staged chunk
   constexpr int NW = NT / 32;
   constexpr int R = (NT / 64) * TM;
+  constexpr int MT = R / 16;
+  constexpr int NTW = (kNC / 8) / NW;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int lr = lane >> 3, lc = lane & 7;
+  const int g = lane >> 2, t = lane & 3;
   const int nnc = ceil_div(N, NR), nkc = ceil_div(Kout, kNC), total = nnc * nkc;
   const bool vec = ((ldw & 3) == 0) && ((reinterpret_cast<uintptr_t>(Wg) & 15) == 0);
+  const int rot = blockIdx.x % nnc;
 
   // staging map: thread -> (quad lq of the 256-wide row, rows lr0, lr0+RPI, ...)
   constexpr int QPRB = kNC / 4;
@@ -301,10 +234,10 @@ __device__ __noinline__ void tile_linear_bwd(const float* __restrict__ dZs, int 
   const int lq = tid % QPRB, lr0 = tid / QPRB;
   auto load_chunk = [&](int c, int stage) {
     const int kci = c / nnc, nci = c - kci * nnc;
-    const int k0 = kci * kNC, n0 = nci * NR;
+    const int k0 = kci * kNC, n0 = ((nci + rot) % nnc) * NR;
     float* dst = Wst + stage * STAGE;
     const int k = k0 + 4 * lq;
-    if (k < round_up4(Kout)) {
+    if (k < ((Kout - k0 + 7) & ~7) + k0) {
       const bool fast = vec && (k + 3 < Kout);
 #pragma unroll
       for (int it = 0; it < (NR + RPI - 1) / RPI; ++it) {
@@ -330,23 +263,21 @@ __device__ __noinline__ void tile_linear_bwd(const float* __restrict__ dZs, int 
     }
   };
 
-  float acc[4][4];
+  float acc[MT][NTW][4];
   load_chunk(0, 0);
   cp_async_commit();
   for (int c = 0; c < total; ++c) {
     const int kci = c / nnc, nci = c - kci * nnc;
-    const int k0 = kci * kNC, n0 = nci * NR;
-    const int kcols = min(kNC, round_up4(Kout - k0));
-    const int WC = pick_wc(kcols), WR = NW / WC;
-    const int wr = warp / WC, wc = warp - wr * WC;
-    const int rpw = R / WR;
-    const int row0 = wr * rpw + lr;
-    const int ccol = wc * 32 + 4 * lc;   // chunk-relative first column of this thread
+    const int k0 = kci * kNC, n0 = ((nci + rot) % nnc) * NR;
+    const int kcols = min(kNC, Kout - k0);
+    const int ntiles = ceil_div(kcols, 8);
     if (nci == 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int m = 0; m < MT; ++m)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < NTW; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.f;
     }
     if (c + 1 < total) {
       load_chunk(c + 1, (c + 1) & 1);
@@ -357,39 +288,76 @@ __device__ __noinline__ void tile_linear_bwd(const float* __restrict__ dZs, int 
     }
     __syncthreads();
     const float* Ws = Wst + (c & 1) * STAGE;
-    const bool active = ccol < kcols;
-    if (active) {
-      const int nlen = min(NR, round_up4(N - n0));
-      const float* zrow = dZs + row0 * ldz + n0;
-      const float* wcol = Ws + ccol;
-      if (rpw == 16) bwd_inner<4>(acc, zrow, 4 * ldz, wcol, LW, nlen);
-      else if (rpw == 8) bwd_inner<2>(acc, zrow, 4 * ldz, wcol, LW, nlen);
-      else bwd_inner<1>(acc, zrow, 4 * ldz, wcol, LW, nlen);
-    }
-    if (nci == nnc - 1 && active) {
-      const int tme = rpw >> 2;
-      const int kcol = k0 + ccol;
+    if (warp < ntiles) {
+      const int nlen = min(NR, (N - n0 + 7) & ~7);
+      const float* zb = dZs + g * ldz + n0 + t;
+      for (int nn = 0; nn < nlen; nn += 8) {
+        uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (i < tme) {
-          const int r = row0 + 4 * i;
-          float o[4];
+        for (int m = 0; m < MT; ++m) {
+          const float* zp = zb + m * 16 * ldz + nn;
+          split_tf32(zp[0], ah[m][0], al[m][0]);
+          split_tf32(zp[8 * ldz], ah[m][1], al[m][1]);
+          split_tf32(zp[4], ah[m][2], al[m][2]);
+          split_tf32(zp[8 * ldz + 4], ah[m][3], al[m][3]);
+        }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int k = kcol + j;
-            float g = 0.f;
-            if (k < Kout) {
-              g = acc[i][j];
-              if (Hs != nullptr) g *= act_bwd_from_out(Hs[r * ldh + k], hact);
-            }
-            o[j] = g;
+        for (int j = 0; j < NTW; ++j) {
+          const int nt = warp + j * NW;
+          if (nt < ntiles) {
+            const float* bp = Ws + (nn + t) * LW + nt * 8 + g;
+            uint32_t bh[2], bl[2];
+            split_tf32(bp[0], bh[0], bl[0]);
+            split_tf32(bp[4 * LW], bh[1], bl[1]);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) mma_3xtf32(acc[m][j], ah[m], al[m], bh, bl);
           }
-          *reinterpret_cast<float4*>(dAs + r * lda + kcol) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+    if (nci == nnc - 1) {
+      const int k4 = round_up4(Kout);
+#pragma unroll
+      for (int j = 0; j < NTW; ++j) {
+        const int nt = warp + j * NW;
+        if (nt < ntiles) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int k = k0 + nt * 8 + 2 * t + e;
+            if (k < k4) {
+#pragma unroll
+              for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                  const int r = m * 16 + g + 8 * hrow;
+                  float gv = 0.f;
+                  if (k < Kout) {
+                    gv = acc[m][j][2 * hrow + e];
+                    if (Hs != nullptr) gv *= act_bwd_from_out(Hs[r * ldh + k], hact);
+                  }
+                  dAs[r * lda + k] = gv;
+                }
+              }
+            }
+          }
         }
       }
     }
     __syncthreads();
   }
+}
+
+// zero a shared-memory region (all NT threads): activations tiles must be finite everywhere
+// because the MMA consumes their padding columns against zero-filled weights.
+template <int NT>
+__device__ __forceinline__ void tile_smem_zero_all(float* smem) {
+  unsigned nbytes;
+  asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(nbytes));
+  const int nfloats = (int)(nbytes / 4);
+  for (int i = threadIdx.x * 4; i + 3 < nfloats; i += NT * 4)
+    *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (threadIdx.x < (nfloats & 3)) smem[(nfloats & ~3) + threadIdx.x] = 0.f;
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------
