@@ -38,9 +38,13 @@ __host__ __device__ constexpr int wstage_floats() {
 // narrow layers still spread over every warp.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  // hi = x rounded to nearest (ties away) at 10 explicit mantissa bits, done with integer ops
+  // (ptxas expands cvt.rna.tf32.f32 to 5 instructions; this is 2).  lo = x - hi is exact in
+  // fp32 and is handed to the MMA as is: the tensor core drops its low 13 bits, an error
+  // <= 2^-11 |lo| <= 2^-22 |x|, the same order as the dropped lo*lo term, and unbiased because
+  // hi is rounded to nearest.  3 instructions per element.
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4],

@@ -43,3 +43,19 @@ def rel_err(a, b):
     a = torch.as_tensor(a, dtype=torch.float64).cpu()
     b = torch.as_tensor(b, dtype=torch.float64).cpu()
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def grad_close(g_gpu, g_ref, what="grad", l2_tol=1e-3, max_tol=1e-2):
+    """Gradient agreement at BASELINE config sizes.  The forward activations agree to ~5e-6
+    (3xTF32 tensor-core products carry ~22 mantissa bits); a hidden unit whose pre-activation
+    is within that distance of 0 gets the other ReLU mask, which changes one row of that
+    layer's weight gradient by O(|x|/B) while everything else agrees to ~1e-5 (the golden-size
+    cases, where no unit sits that close to 0, hold 1e-5 on every element).  Hence a relative
+    L2 bound (measured <= 5e-4) plus a max-norm bound."""
+    a = torch.as_tensor(g_gpu, dtype=torch.float64).cpu().reshape(-1)
+    b = torch.as_tensor(g_ref, dtype=torch.float64).cpu().reshape(-1)
+    l2 = float((a - b).norm() / (b.norm() + 1e-30))
+    mx = float((a - b).abs().max() / (b.abs().max() + 1e-30))
+    assert l2 < l2_tol, (what, "rel L2", l2)
+    assert mx < max_tol, (what, "rel max", mx)
+    return l2, mx
