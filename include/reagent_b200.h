@@ -140,7 +140,7 @@ typedef struct rb200_dqn_args {
   float* td_target;              /* [B] or NULL                                */
   float* q_selected;             /* [B] or NULL                                */
   int32_t* next_action_idx;      /* [B] argmax index or NULL                   */
-  float* loss_partials;          /* [>= rb200_dqn_num_tiles(B)]                */
+  float* loss_partials;          /* [>= ceil(B/16)]                */
   float* loss;                   /* [1] mean loss (written by the last tile)   */
   uint32_t* tile_counter;        /* [1] zero-initialised scratch, self-resetting */
 } rb200_dqn_args_t;

@@ -171,11 +171,21 @@ struct AdamDev {
 
 __global__ void __launch_bounds__(256) adam_soft_kernel(const AdamDev d) {
   const rb200_adam_args_t& a = d.a;
-  const long long t = *a.step + 1;
-  const double bc1 = 1.0 - pow(a.beta1, (double)t);
-  const double bc2 = 1.0 - pow(a.beta2, (double)t);
-  const float step_size = (float)(a.lr / bc1);
-  const float bc2_sqrt = (float)sqrt(bc2);
+  // bias corrections in double like torch (Python floats), once per block
+  __shared__ long long s_t;
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const long long tt = *a.step + 1;
+    const double bc1 = 1.0 - pow(a.beta1, (double)tt);
+    const double bc2 = 1.0 - pow(a.beta2, (double)tt);
+    s_t = tt;
+    s_step_size = (float)(a.lr / bc1);
+    s_bc2_sqrt = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const long long t = s_t;
+  const float step_size = s_step_size;
+  const float bc2_sqrt = s_bc2_sqrt;
   const float eps = (float)a.eps;
   const float w1 = (float)(1.0 - a.beta1);
   const float b2 = (float)a.beta2;

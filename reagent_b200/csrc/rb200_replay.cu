@@ -20,6 +20,7 @@
 namespace rb200 {
 
 constexpr int kSPB = 32;  // samples per CTA
+constexpr int kTopLevels = 11;
 
 struct SampleDev {
   rb200_sample_args_t a;
@@ -35,9 +36,18 @@ __global__ void __launch_bounds__(kThreads) replay_sample_kernel(const SampleDev
   __shared__ long long s_idx[kSPB];
   __shared__ long long s_next[kSPB];
   __shared__ int s_term[kSPB];
+  // top kTopLevels levels of the fp64 sum tree (2^kTopLevels - 1 nodes, 16 KB): loaded once
+  // per CTA with coalesced reads so that only the deep levels cost a dependent L2 round trip
+  __shared__ double s_top[(1 << kTopLevels) - 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b0 = blockIdx.x * kSPB;
   const long long cap = a.capacity;
+  if (a.mode == RB200_SAMPLE_PRIORITIZED) {
+    const int top = min(a.tree_depth + 1, kTopLevels);
+    const int n_top = (1 << top) - 1;
+    for (int i = tid; i < n_top; i += kThreads) s_top[i] = __ldg(a.tree + i);
+    __syncthreads();
+  }
 
   if (warp == 0) {
     const int b = b0 + lane;
@@ -45,11 +55,12 @@ __global__ void __launch_bounds__(kThreads) replay_sample_kernel(const SampleDev
       long long idx = 0;
       if (a.mode == RB200_SAMPLE_PRIORITIZED) {
         // sum_tree.py:112-131: q *= root; descend comparing with the left child
-        double q = a.query[b] * a.tree[0];
+        double q = a.query[b] * s_top[0];
         long long node = 0;
         for (int lvl = 1; lvl <= a.tree_depth; ++lvl) {
           const long long left = node * 2;
-          const double left_sum = __ldg(a.tree + ((1ll << lvl) - 1) + left);
+          const long long pos = ((1ll << lvl) - 1) + left;
+          const double left_sum = (lvl < kTopLevels) ? s_top[pos] : __ldg(a.tree + pos);
           if (q < left_sum) {
             node = left;
           } else {

@@ -1,0 +1,121 @@
+"""Host-side API surface (no GPU): constructors, optimizer order, yield contract metadata,
+C-ABI symbols, loud failure without CUDA."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from reagent_b200 import _lib
+
+    lib = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "reagent_b200.h")).read()
+    names = set(re.findall(r"\b(rb200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 20
+    for n in sorted(names):
+        assert hasattr(lib, n), f"libreagent_b200.so does not export {n}"
+    assert lib.rb200_version() >= 1
+
+
+def test_trainer_constructors_and_optimizer_order():
+    from reagent_b200.core import types as rlt
+    from reagent_b200.core.parameters import EvaluationParameters
+    from reagent_b200.models import (FullyConnectedActor, FullyConnectedCritic, FullyConnectedDQN,
+                                     GaussianFullyConnectedActor)
+    from reagent_b200.optimizer import FusedAdam, SoftUpdate
+    from reagent_b200.training import DQNTrainer, QRDQNTrainer, SACTrainer, TD3Trainer
+
+    ev = EvaluationParameters(calc_cpe_in_training=False)
+    q = FullyConnectedDQN(8, 3, [16], ["relu"])
+    t = DQNTrainer(q, q.get_target_network(), actions=["a", "b", "c"], evaluation=ev)
+    assert [type(o) for o in t.optimizers()] == [FusedAdam, SoftUpdate]
+    assert inspect.signature(t.train_step_gen).parameters["training_batch"].annotation is rlt.DiscreteDqnInput
+    with pytest.raises(NotImplementedError):
+        DQNTrainer(q, q.get_target_network(), actions=["a", "b", "c"])  # CPE on by default
+    qq = FullyConnectedDQN(8, 3, [16], ["relu"], num_atoms=5)
+    tq = QRDQNTrainer(qq, qq.get_target_network(), actions=["a", "b", "c"], num_atoms=5, evaluation=ev)
+    assert tq.quantiles.shape == (1, 5) and abs(float(tq.quantiles[0, 0]) - 0.1) < 1e-7
+    c1, c2 = FullyConnectedCritic(8, 2, [16], ["relu"]), FullyConnectedCritic(8, 2, [16], ["relu"])
+    ts = SACTrainer(GaussianFullyConnectedActor(8, 2, [16], ["relu"]), c1, c2)
+    assert [type(o) for o in ts.optimizers()] == [FusedAdam] * 4 + [SoftUpdate]
+    assert inspect.signature(ts.train_step_gen).parameters["training_batch"].annotation is rlt.PolicyNetworkInput
+    ts2 = SACTrainer(GaussianFullyConnectedActor(8, 2, [16], ["relu"]), c1, None, alpha_optimizer=None)
+    assert len(ts2.optimizers()) == 3
+    tt = TD3Trainer(FullyConnectedActor(8, 2, [16], ["relu"]), c1, c2)
+    assert [type(o) for o in tt.optimizers()] == [FusedAdam] * 3 + [SoftUpdate]
+
+
+def test_state_dict_keys_match_reference_layout():
+    from reagent_b200.models import FullyConnectedDQN
+
+    q = FullyConnectedDQN(4, 2, [8, 6], ["relu", "tanh"])
+    assert list(q.state_dict().keys()) == [
+        "fc.dnn.0.0.weight", "fc.dnn.0.0.bias", "fc.dnn.1.0.weight", "fc.dnn.1.0.bias",
+        "fc.dnn.2.0.weight", "fc.dnn.2.0.bias"]
+    # parameters are views into one flat arena; deepcopy gets its own arena
+    base = q.arena.flat.data_ptr()
+    assert q.fc.dnn[0][0].weight.data_ptr() == base
+    qt = q.get_target_network()
+    assert qt.arena.flat.data_ptr() != base and torch.equal(qt.arena.flat, q.arena.flat)
+    sd = {k: torch.randn_like(v) for k, v in q.state_dict().items()}
+    q.load_state_dict(sd)
+    assert torch.equal(q.fc.dnn[1][0].weight, sd["fc.dnn.1.0.weight"])
+    assert q.fc.dnn[1][0].weight.data_ptr() != q.fc.dnn[0][0].weight.data_ptr()
+    a = q.arena
+    assert torch.equal(a.flat[a.w_off[1]: a.w_off[1] + 48].view(6, 8), sd["fc.dnn.1.0.weight"])
+
+
+def test_no_cpu_fallback():
+    from reagent_b200 import _lib
+    from reagent_b200.core import types as rlt
+    from reagent_b200.models import FullyConnectedDQN
+    from reagent_b200.preprocessing import Preprocessor
+    from reagent_b200.core.parameters import NormalizationParameters as NP
+
+    q = FullyConnectedDQN(4, 2, [8], ["relu"])
+    with pytest.raises(_lib.Rb200Error):
+        q(rlt.FeatureData(torch.randn(3, 4)))
+    p = Preprocessor({1: NP("CONTINUOUS", mean=0.0, stddev=1.0)})
+    with pytest.raises(_lib.Rb200Error):
+        p(torch.randn(3, 1), torch.ones(3, 1))
+
+
+def test_net_builders_and_managers_construct():
+    from reagent_b200.core.parameters import NormalizationData, NormalizationParameters as NP
+    from reagent_b200.net_builder import FullyConnected, GaussianFullyConnected, ParametricFullyConnected, Quantile
+
+    s = NormalizationData({i: NP("CONTINUOUS", mean=0.0, stddev=1.0) for i in range(6)})
+    a = NormalizationData({i: NP("CONTINUOUS_ACTION", min_value=-1.0, max_value=1.0) for i in range(2)})
+    assert FullyConnected(sizes=[8], activations=["relu"]).build_q_network(None, s, 3).fc.layers == [6, 8, 3]
+    assert Quantile(sizes=[8], activations=["relu"]).build_q_network(s, 3, 5).fc.layers == [6, 8, 15]
+    assert ParametricFullyConnected().build_q_network(s, a).fc.layers == [8, 128, 64, 1]
+    assert GaussianFullyConnected().build_actor(None, s, a).fc.layers == [6, 128, 64, 4]
+    from reagent_b200.model_managers import DiscreteDQN
+    with pytest.raises(RuntimeError):
+        DiscreteDQN(actions=["0", "1"]).build_trainer({"state": s}, use_gpu=False)
+
+
+def test_input_makers_match_reference_formulas():
+    import collections
+
+    from reagent_b200.gym.preprocessors.trainer_preprocessor import (DiscreteDqnInputMaker,
+                                                                    PolicyNetworkInputMaker)
+
+    B = collections.namedtuple("b", ["state", "action", "reward", "next_state", "next_action", "terminal"])
+    b = B(torch.randn(4, 3), torch.tensor([[0], [2], [1], [2]]), torch.randn(4, 1), torch.randn(4, 3),
+          torch.tensor([[1], [0], [2], [1]]), torch.tensor([[False], [True], [False], [False]]))
+    out = DiscreteDqnInputMaker(3)(b)
+    assert out.action.tolist() == [[1, 0, 0], [0, 0, 1], [0, 1, 0], [0, 0, 1]]
+    assert out.next_action.tolist() == [[0, 1, 0], [0, 0, 0], [0, 0, 1], [0, 1, 0]]
+    assert out.not_terminal.reshape(-1).tolist() == [1, 0, 1, 1]
+    bc = B(torch.randn(2, 3), torch.tensor([[0.0, 2.0], [1.0, -2.0]]), torch.randn(2, 1), torch.randn(2, 3),
+           torch.tensor([[2.0, 2.0], [0.0, 0.0]]), torch.tensor([[True], [False]]))
+    oc = PolicyNetworkInputMaker([-2.0, -2.0], [2.0, 2.0])(bc)
+    assert oc.action.float_features.tolist() == [[0.0, 1.0], [0.5, -1.0]]
+    assert oc.next_action.float_features.tolist() == [[0.0, 0.0], [0.0, 0.0]]
