@@ -7,13 +7,15 @@ namespace rb200 {
 
 // ---------------------------------------------------------------------------
 // dW_l[n,k] = sum_b dZ_l[b,n] * A_{l-1}[b,k];  db_l[n] = sum_b dZ_l[b,n]
-// One CTA = one 64(n) x 64(k) tile of one layer over one batch split.
-// 256 threads, each 4(n) x 4(k) outputs; per batch row a thread issues 2 LDS.128
-// (dz quad broadcast across the 16 threads that share it, a quad conflict-free)
-// for 16 FMAs.  Deterministic: partial s of the split-K sum goes to its own slab.
+// One CTA = one 64(n) x 64(k) tile of one layer over one batch split; 8 warps, each a
+// 32(n) x 16(k) block = 2x2 mma.sync.m16n8k8 tiles, contraction over 8 batch rows per step,
+// 3xTF32 error compensation like the row-tile kernels.  Operands are staged [batch][64+8]
+// (stride == 8 mod 32): the A fragment (dZ^T: row n, col b) and the B fragment (row b, col k)
+// are conflict-free LDS.32.  Deterministic: split s of the batch sum goes to its own slab.
 // ---------------------------------------------------------------------------
 constexpr int kWgTile = 64;
 constexpr int kWgRows = 32;  // batch rows staged per step
+constexpr int kWgLd = kWgTile + 8;
 
 struct WgradLayer {
   const float* A;   // [B, K] input activations of this layer
@@ -30,35 +32,48 @@ struct WgradParams {
   long long P;
 };
 
+__device__ __forceinline__ void wg_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void wg_mma(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+      "{%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 __global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradParams p) {
-  __shared__ __align__(16) float zs[2][kWgRows][kWgTile + 4];
-  __shared__ __align__(16) float as[2][kWgRows][kWgTile + 4];
+  __shared__ __align__(16) float zs[2][kWgRows][kWgLd];
+  __shared__ __align__(16) float as[2][kWgRows][kWgLd];
   int li = 0;
   while (li + 1 < p.n_layers && (int)blockIdx.x >= p.L[li + 1].tile_start) ++li;
   const WgradLayer& Ly = p.L[li];
-  const int t = blockIdx.x - Ly.tile_start;
-  const int tn = t / Ly.tiles_k, tk = t - tn * Ly.tiles_k;
+  const int tl = blockIdx.x - Ly.tile_start;
+  const int tn = tl / Ly.tiles_k, tk = tl - tn * Ly.tiles_k;
   const int n0 = tn * kWgTile, k0 = tk * kWgTile;
   const int split = blockIdx.y;
   const int b_begin = split * p.rows_per_split;
   const int b_end = min(p.B, b_begin + p.rows_per_split);
-  const int tid = threadIdx.x;
-  const int in_ = tid >> 4, ik = tid & 15;  // thread owns n = n0+4*in_.., k = k0+4*ik..
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wn = (warp >> 2) * 32;  // warp block origin inside the 64x64 tile
+  const int wk = (warp & 3) * 16;
   const int N = Ly.N, K = Ly.K;
   const bool vz = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(Ly.dZ) & 15) == 0);
   const bool va = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(Ly.A) & 15) == 0);
 
-  float acc[4][4];
-  float bsum[4];
+  float acc[2][2][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    bsum[i] = 0.f;
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  }
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+  float bsum = 0.f;  // thread tid < 64: column sum of dZ for n0 + tid (bias gradient)
 
   auto stage = [&](int b0, int buf) {
-    // 32 rows x 16 quads for each operand = 512 quads each; 256 threads -> 2 + 2
     for (int idx = tid; idx < kWgRows * 16; idx += kThreads) {
       const int r = idx >> 4, qd = idx & 15;
       const int b = b0 + r;
@@ -114,35 +129,51 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradParams p) {
     }
     __syncthreads();
     const int buf = s & 1;
+#pragma unroll
+    for (int bb = 0; bb < kWgRows; bb += 8) {
+      // A = dZ^T block: element (row n, col b) = zs[b][n]
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int n = wn + 16 * i + g;
+        wg_split(zs[buf][bb + t][n], ah[i][0], al[i][0]);
+        wg_split(zs[buf][bb + t][n + 8], ah[i][1], al[i][1]);
+        wg_split(zs[buf][bb + t + 4][n], ah[i][2], al[i][2]);
+        wg_split(zs[buf][bb + t + 4][n + 8], ah[i][3], al[i][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k = wk + 8 * j + g;
+        uint32_t bh[2], bl[2];
+        wg_split(as[buf][bb + t][k], bh[0], bl[0]);
+        wg_split(as[buf][bb + t + 4][k], bh[1], bl[1]);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          wg_mma(acc[i][j], al[i], bh);
+          wg_mma(acc[i][j], ah[i], bl);
+          wg_mma(acc[i][j], ah[i], bh);
+        }
+      }
+    }
+    if (tk == 0 && tid < kWgTile) {
 #pragma unroll 8
-    for (int r = 0; r < kWgRows; ++r) {
-      const float4 z = *reinterpret_cast<const float4*>(&zs[buf][r][4 * in_]);
-      const float4 x = *reinterpret_cast<const float4*>(&as[buf][r][4 * ik]);
-      acc[0][0] = fmaf(z.x, x.x, acc[0][0]); acc[0][1] = fmaf(z.x, x.y, acc[0][1]);
-      acc[0][2] = fmaf(z.x, x.z, acc[0][2]); acc[0][3] = fmaf(z.x, x.w, acc[0][3]);
-      acc[1][0] = fmaf(z.y, x.x, acc[1][0]); acc[1][1] = fmaf(z.y, x.y, acc[1][1]);
-      acc[1][2] = fmaf(z.y, x.z, acc[1][2]); acc[1][3] = fmaf(z.y, x.w, acc[1][3]);
-      acc[2][0] = fmaf(z.z, x.x, acc[2][0]); acc[2][1] = fmaf(z.z, x.y, acc[2][1]);
-      acc[2][2] = fmaf(z.z, x.z, acc[2][2]); acc[2][3] = fmaf(z.z, x.w, acc[2][3]);
-      acc[3][0] = fmaf(z.w, x.x, acc[3][0]); acc[3][1] = fmaf(z.w, x.y, acc[3][1]);
-      acc[3][2] = fmaf(z.w, x.z, acc[3][2]); acc[3][3] = fmaf(z.w, x.w, acc[3][3]);
-      bsum[0] += z.x; bsum[1] += z.y; bsum[2] += z.z; bsum[3] += z.w;
+      for (int r = 0; r < kWgRows; ++r) bsum += zs[buf][r][tid];
     }
     __syncthreads();
   }
 
-  float* g = p.gpart + (size_t)split * p.P;
+  float* gp = p.gpart + (size_t)split * p.P;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int n = n0 + 4 * in_ + i;
-    if (n >= N) continue;
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = k0 + 4 * ik + j;
-      if (k < K) g[Ly.w_off + (size_t)n * K + k] = acc[i][j];
-    }
-    if (tk == 0 && ik == 0) g[Ly.b_off + n] = bsum[i];
-  }
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = n0 + wn + 16 * i + g + ((e >> 1) ? 8 : 0);
+        const int k = k0 + wk + 8 * j + 2 * t + (e & 1);
+        if (n < N && k < K) gp[Ly.w_off + (size_t)n * K + k] = acc[i][j][e];
+      }
+  if (tk == 0 && tid < kWgTile && n0 + tid < N) gp[Ly.b_off + n0 + tid] = bsum;
 }
 
 // g[i] = sum_s gpart[s*P + i]
@@ -194,8 +225,17 @@ __global__ void __launch_bounds__(256) adam_soft_kernel(const AdamDev d) {
   const long long n = a.n;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    float g = a.grad[i];
-    for (int s = 1; s < a.splits; ++s) g += a.grad[(size_t)s * n + i];
+    // split-K partials: loads issued 8 at a time, summed in slab order (deterministic)
+    float g = 0.f;
+    for (int s0 = 0; s0 < a.splits; s0 += 8) {
+      float part[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        part[u] = (s0 + u < a.splits) ? a.grad[(size_t)(s0 + u) * n + i] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (s0 + u < a.splits) g = (s0 + u == 0) ? part[u] : g + part[u];
+    }
     g *= a.grad_scale;
     float p = a.params[i];
     if (wd != 0.f) g = fmaf(wd, p, g);

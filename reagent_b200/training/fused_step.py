@@ -99,18 +99,43 @@ class FusedDqnStep:
         return s["loss_host"]
 
 
-def capture_device_only(trainer, rb, batch_size, steps, queries_dev, process_group=None):
+def capture_device_only(trainer, rb, batch_size, steps, queries_dev, process_group=None,
+                        overlap_sampling=True):
     """`steps` consecutive updates in ONE graph with all random numbers already resident in
     HBM (queries_dev[k] is the k-th update's draw) -- the kernel-only measurement of
-    bench.py.  Returns (graph, list of per-update (start, end) event pairs or None)."""
+    bench.py.  With `overlap_sampling` the replay-sample kernel of update k+1 is captured on a
+    second stream and runs concurrently with the TD / weight-gradient / Adam kernels of update
+    k (the row-tile kernels leave ~20 SMs and most of HBM idle; sampling does not depend on
+    the parameters, and no trainer of the path writes priorities back -- SURVEY.md fact 5)."""
     A = trainer.num_actions
     prioritized = isinstance(rb, PrioritizedReplayBuffer)
+
+    def sample(k):
+        if prioritized:
+            return rb.sample_discrete_dqn_batch(batch_size, A, query_dev=queries_dev[k])
+        return rb.sample_discrete_dqn_batch(batch_size, A, ranks_dev=queries_dev[k])
+
     g = torch.cuda.CUDAGraph()
+    keep = []  # every batch stays alive until the capture ends: no cross-stream block reuse
+    side = torch.cuda.Stream()
     with torch.cuda.graph(g):
+        main = torch.cuda.current_stream()
+        batch = sample(0)
+        keep.append(batch)
         for k in range(steps):
-            if prioritized:
-                batch = rb.sample_discrete_dqn_batch(batch_size, A, query_dev=queries_dev[k])
-            else:
-                batch = rb.sample_discrete_dqn_batch(batch_size, A, ranks_dev=queries_dev[k])
+            nxt = None
+            if overlap_sampling and k + 1 < steps:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    nxt = sample(k + 1)
+                keep.append(nxt)
             trainer.train_batch(batch, process_group=process_group)
+            if k + 1 < steps:
+                if nxt is None:
+                    nxt = sample(k + 1)
+                    keep.append(nxt)
+                else:
+                    main.wait_stream(side)
+                batch = nxt
+    g._rb200_keep = keep
     return g

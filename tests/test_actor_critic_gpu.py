@@ -188,11 +188,11 @@ def test_td3_matches_reference(name, fast):
 
 
 def _adam_close(w_gpu, w_ref, meta):
+    """Post-Adam parameters at config sizes: every element within the total step budget
+    (n_updates * 2 * lr) and the typical element within 2 % of one step."""
     d = (w_gpu.detach().cpu().double() - w_ref.detach().double()).abs()
-    scale = float(w_ref.detach().abs().max())
     assert float(d.max()) <= 2.0 * meta["n_updates"] * meta["lr"] * 1.01
-    frac_off = float((d > 1e-5 * scale).double().mean())
-    assert frac_off < 0.1, frac_off
+    assert float(d.median()) < 0.02 * meta["lr"], float(d.median())
 
 
 def _rand_net(dims, acts, gen, bias=0.05):
