@@ -183,6 +183,10 @@ typedef struct rb200_qrdqn_args {
 
 int rb200_linear_forward(const float* W, const float* b, int32_t act, int32_t K, int32_t N,
                          const float* in, int32_t batch, float* out, void* stream);
+/* tcgen05.mma (kind::tf32, 3xTF32) + TMEM implementation of rb200_linear_forward, taken
+ * automatically for batch >= 128 and N >= 128 */
+int rb200_linear_forward_tc(const float* W, const float* b, int32_t act, int32_t K, int32_t N,
+                            const float* in, int32_t batch, float* out, void* stream);
 int rb200_linear_backward_dx(const float* W, int32_t K, int32_t N, const float* dz,
                              const float* h_prev, int32_t act_prev, int32_t batch, float* out,
                              void* stream);

@@ -253,10 +253,17 @@ RB200_LAUNCH_GENERIC(mlp_bwd_rows_kernel, mlpbwd)
 
 using namespace rb200;
 
+extern "C" int rb200_linear_forward_tc(const float* W, const float* b, int32_t act, int32_t K,
+                                       int32_t N, const float* in, int32_t batch, float* out,
+                                       void* stream);
+
 extern "C" int rb200_linear_forward(const float* W, const float* b, int32_t act, int32_t K,
                                     int32_t N, const float* in, int32_t batch, float* out,
                                     void* stream) {
   if (!W || !in || !out || K <= 0 || N <= 0 || batch <= 0) { set_last_error("rb200_linear_forward: bad argument"); return RB200_E_INVALID; }
+  // GEMM-shaped problems (>= one full 128x128 tile) go to the tcgen05 / TMEM kernel
+  static const bool no_tc = getenv("RB200_DISABLE_TCGEN05") != nullptr;  // debugging aid
+  if (!no_tc && batch >= 128 && N >= 128) return rb200_linear_forward_tc(W, b, act, K, N, in, batch, out, stream);
   LinFwdDev p{in, K, W, b, N, act, out, batch, 0, kColBlock + 4};
   RowsCfg cfg = pick_rows_cfg(batch, K, 4, 1, 0, p.ld_o, 0);
   if (cfg.tm == 0) { set_last_error("rb200_linear_forward: tile does not fit in shared memory"); return RB200_E_SMEM; }

@@ -1,0 +1,268 @@
+// reagent_b200 -- Blackwell-native wide Linear forward: tcgen05.mma (kind::tf32) with the
+// accumulator in Tensor Memory, 3xTF32 error compensation.
+//
+//   out[B, N] = act(in[B, K] . W[N, K]^T + b)          (nn.Linear forward, wide N)
+//
+// Used for the QR-DQN head ([hidden -> A*N], reagent/models/fully_connected_network.py:
+// 190-217 / reagent/training/qrdqn_trainer.py:125-149): at config 3 it is a
+// 4096 x 6400 x 128 GEMM, the only genuinely GEMM-shaped op of the path.
+//
+// One CTA = one 128 (rows) x 128 (cols) output tile; accumulator D in TMEM (128 lanes x
+// 128 fp32 columns).  K is walked in 32-element chunks through a 2-stage shared-memory ring.
+// Per chunk all 256 threads load 16 B pieces of in / W with coalesced LDG.128, split every
+// value into hi = rna_tf32(x) and lo = x - hi and store both planes in the canonical K-major
+// no-swizzle UMMA layout  [k/4][row][4 floats]  (core matrix = 8 rows x 16 B contiguous;
+// SBO = 128 B between 8-row groups, LBO = rows*16 B between the two 16-byte k-slices of one
+// K=8 MMA).  One elected thread then issues, per K=8 step, the three MMAs
+//   D += A_lo.B_hi ;  D += A_hi.B_lo ;  D += A_hi.B_hi
+// and commits the stage to an mbarrier, which the producers wait on before overwriting it.
+// Epilogue: tcgen05.ld (32x32b.x32) -> bias + activation -> global.
+#include "rb200_common.cuh"
+
+namespace rb200 {
+
+constexpr int kTcM = 128;     // rows per CTA (UMMA M)
+constexpr int kTcN = 128;     // cols per CTA (UMMA N)
+constexpr int kTcKC = 32;     // k elements per stage
+constexpr int kTcThreads = 256;
+constexpr int kTcPlane = kTcM * kTcKC;                 // floats per operand plane per stage
+constexpr int kTcStageFloats = 4 * kTcPlane;           // A_hi, A_lo, B_hi, B_lo
+constexpr size_t kTcSmemBytes = 2 * kTcStageFloats * sizeof(float) + 64;
+
+struct TcDev {
+  const float* in; const float* W; const float* b; float* out;
+  int batch, K, N, act;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// bits [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte
+// offset >> 4, [46,48) version = 1 (sm_100), [61,64) layout type = 0 (no swizzle).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, K-major A and B.
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;                      // c_format = F32
+  d |= 2u << 7;                      // a_format = TF32
+  d |= 2u << 10;                     // b_format = TF32
+  d |= (uint32_t)(N >> 3) << 17;     // n_dim
+  d |= (uint32_t)(M >> 4) << 24;     // m_dim
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (long long it = 0;; ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity));
+    if (ok) break;
+    if (it > 50000000LL) __trap();  // never spin forever on a protocol bug
+  }
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
+      smem_u32(bar)));
+}
+
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+  uint32_t h;
+  h = (__float_as_uint(v.x) + 0x1000u) & 0xffffe000u; hi.x = __uint_as_float(h); lo.x = v.x - hi.x;
+  h = (__float_as_uint(v.y) + 0x1000u) & 0xffffe000u; hi.y = __uint_as_float(h); lo.y = v.y - hi.y;
+  h = (__float_as_uint(v.z) + 0x1000u) & 0xffffe000u; hi.z = __uint_as_float(h); lo.z = v.z - hi.z;
+  h = (__float_as_uint(v.w) + 0x1000u) & 0xffffe000u; hi.w = __uint_as_float(h); lo.w = v.w - hi.w;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_linear_fwd_kernel(const TcDev p) {
+  extern __shared__ __align__(128) float smem[];
+  float* stage0 = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kTcStageFloats);  // [2] stage free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * kTcM, col0 = blockIdx.y * kTcN;
+  const int K = p.K;
+  const int nchunks = ceil_div(K, kTcKC);
+  const bool vin = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0);
+  const bool vw = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0);
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                     smem_u32(tmem_slot)), "n"(kTcN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t idesc = umma_idesc_tf32(kTcM, kTcN);
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c & 1;
+    float* a_hi = stage0 + st * kTcStageFloats;
+    float* a_lo = a_hi + kTcPlane;
+    float* b_hi = a_lo + kTcPlane;
+    float* b_lo = b_hi + kTcPlane;
+    // the MMAs that read this stage two chunks ago must have completed
+    if (c >= 2) mbar_wait(&bars[st], ((c >> 1) - 1) & 1);
+    const int k0 = c * kTcKC;
+    // 128 rows x 8 quads per operand; thread -> (row = idx / 8, quad = idx % 8): a warp reads
+    // 4 rows x 128 B of global memory per instruction
+    for (int idx = tid; idx < kTcM * (kTcKC / 4); idx += kTcThreads) {
+      const int r = idx >> 3, q = idx & 7;
+      const int k = k0 + 4 * q;
+      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int row = row0 + r, col = col0 + r;
+      if (row < p.batch) {
+        const float* s = p.in + (size_t)row * K;
+        if (vin && k + 3 < K) va = __ldg(reinterpret_cast<const float4*>(s + k));
+        else {
+          if (k < K) va.x = s[k];
+          if (k + 1 < K) va.y = s[k + 1];
+          if (k + 2 < K) va.z = s[k + 2];
+          if (k + 3 < K) va.w = s[k + 3];
+        }
+      }
+      if (col < p.N) {
+        const float* s = p.W + (size_t)col * K;
+        if (vw && k + 3 < K) vb = __ldg(reinterpret_cast<const float4*>(s + k));
+        else {
+          if (k < K) vb.x = s[k];
+          if (k + 1 < K) vb.y = s[k + 1];
+          if (k + 2 < K) vb.z = s[k + 2];
+          if (k + 3 < K) vb.w = s[k + 3];
+        }
+      }
+      float4 h, l;
+      const int off = q * (kTcM * 4) + r * 4;  // [k quad][row][4]
+      split4(va, h, l);
+      *reinterpret_cast<float4*>(a_hi + off) = h;
+      *reinterpret_cast<float4*>(a_lo + off) = l;
+      split4(vb, h, l);
+      *reinterpret_cast<float4*>(b_hi + off) = h;
+      *reinterpret_cast<float4*>(b_lo + off) = l;
+    }
+    // make the generic-proxy stores visible to the tensor core (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;\n" ::);
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+      constexpr uint32_t LBO = kTcM * 16;  // bytes between the two 16 B k-slices of one MMA
+      constexpr uint32_t SBO = 128;        // bytes between 8-row groups
+#pragma unroll
+      for (int s = 0; s < kTcKC / 8; ++s) {
+        const uint32_t koff = (uint32_t)(2 * s) * LBO;  // k quad 2s
+        const uint64_t dah = umma_desc(smem_u32(a_hi) + koff, LBO, SBO);
+        const uint64_t dal = umma_desc(smem_u32(a_lo) + koff, LBO, SBO);
+        const uint64_t dbh = umma_desc(smem_u32(b_hi) + koff, LBO, SBO);
+        const uint64_t dbl = umma_desc(smem_u32(b_lo) + koff, LBO, SBO);
+        umma_tf32(tmem_d, dal, dbh, idesc, (c > 0 || s > 0) ? 1u : 0u);
+        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+        umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+      }
+      umma_commit(&bars[st]);
+    }
+    // no barrier here: the next chunk writes the other stage; its own mbarrier protects it
+  }
+  // wait for the last commit (covers all earlier MMAs of this thread as well)
+  {
+    const int last = nchunks - 1;
+    mbar_wait(&bars[last & 1], (last >> 1) & 1);
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+
+  // ---- epilogue: TMEM -> registers -> bias + activation -> global ----
+  // warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); warps 0-3 take columns [0,64),
+  // warps 4-7 columns [64,128)
+  {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int row = row0 + r;
+    for (int cb = (warp >> 2) * 64; cb < (warp >> 2) * 64 + 64; cb += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)cb;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+          "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+            "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+            "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+            "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+            "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::);
+      if (row < p.batch) {
+        float* orow = p.out + (size_t)row * p.N;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + cb + j;
+          if (col < p.N) {
+            const float bias = p.b ? __ldg(p.b + col) : 0.f;
+            orow[col] = act_fwd(__uint_as_float(v[j]) + bias, p.act);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "n"(kTcN));
+  }
+}
+
+}  // namespace rb200
+
+using namespace rb200;
+
+// Same contract as rb200_linear_forward; chosen by it for large shapes.
+extern "C" int rb200_linear_forward_tc(const float* W, const float* b, int32_t act, int32_t K,
+                                       int32_t N, const float* in, int32_t batch, float* out,
+                                       void* stream) {
+  if (!W || !in || !out || K <= 0 || N <= 0 || batch <= 0) { set_last_error("rb200_linear_forward_tc: bad argument"); return RB200_E_INVALID; }
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_linear_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tc_linear_fwd)");
+    configured = true;
+  }
+  TcDev p{in, W, b, out, batch, K, N, act};
+  dim3 grid(ceil_div(batch, kTcM), ceil_div(N, kTcN));
+  tc_linear_fwd_kernel<<<grid, kTcThreads, kTcSmemBytes, (cudaStream_t)stream>>>(p);
+  return check_cuda(cudaGetLastError(), "tc_linear_fwd_kernel launch");
+}
