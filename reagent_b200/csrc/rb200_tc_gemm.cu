@@ -8,12 +8,14 @@
 // 4096 x 6400 x 128 GEMM, the only genuinely GEMM-shaped op of the path.
 //
 // One CTA = one 128 (rows) x 128 (cols) output tile; accumulator D in TMEM (128 lanes x
-// 128 fp32 columns).  K is walked in 32-element chunks through a 2-stage shared-memory ring.
-// Per chunk all 256 threads load 16 B pieces of in / W with coalesced LDG.128, split every
+// 128 fp32 columns).  K is walked in 32-element chunks through ONE shared-memory stage; the
+// next chunk's global loads are held in registers while the tensor core consumes the stage, and
+// two CTAs share an SM so that one CTA's loads overlap the other's MMAs / epilogue.
+// Per chunk all 256 threads load 16 B pieces of in / W with LDG.128, split every
 // value into hi = rna_tf32(x) and lo = x - hi and store both planes in the canonical K-major
 // no-swizzle UMMA layout  [k/4][row][4 floats]  (core matrix = 8 rows x 16 B contiguous;
-// SBO = 128 B between 8-row groups, LBO = rows*16 B between the two 16-byte k-slices of one
-// K=8 MMA).  One elected thread then issues, per K=8 step, the three MMAs
+// SBO = 128 B between 8-row groups, LBO = rows*16 B + 16 B pad between the two 16-byte
+// k-slices of one K=8 MMA).  One elected thread then issues, per K=8 step, the three MMAs
 //   D += A_lo.B_hi ;  D += A_hi.B_lo ;  D += A_hi.B_hi
 // and commits the stage to an mbarrier, which the producers wait on before overwriting it.
 // Epilogue: tcgen05.ld (32x32b.x32) -> bias + activation -> global.
@@ -25,9 +27,13 @@ constexpr int kTcM = 128;     // rows per CTA (UMMA M)
 constexpr int kTcN = 128;     // cols per CTA (UMMA N)
 constexpr int kTcKC = 32;     // k elements per stage
 constexpr int kTcThreads = 256;
-constexpr int kTcPlane = kTcM * kTcKC;                 // floats per operand plane per stage
+constexpr int kTcQuadStride = kTcM * 4 + 4;            // floats between k quads: 2048 B + 16 B pad
+constexpr int kTcPlane = (kTcKC / 4) * kTcQuadStride;  // floats per operand plane per stage
 constexpr int kTcStageFloats = 4 * kTcPlane;           // A_hi, A_lo, B_hi, B_lo
-constexpr size_t kTcSmemBytes = 2 * kTcStageFloats * sizeof(float) + 64;
+constexpr int kTcLdo = kTcN + 4;                       // padded stride of the epilogue tile
+constexpr int kTcBufFloats = (kTcM * kTcLdo > kTcStageFloats) ? kTcM * kTcLdo : kTcStageFloats;
+constexpr size_t kTcSmemBytes = kTcBufFloats * sizeof(float) + 64;
+constexpr int kTcIters = kTcM * (kTcKC / 4) / kTcThreads;  // 16 B pieces per thread per operand
 
 struct TcDev {
   const float* in; const float* W; const float* b; float* out;
@@ -103,11 +109,16 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
   h = (__float_as_uint(v.w) + 0x1000u) & 0xffffe000u; hi.w = __uint_as_float(h); lo.w = v.w - hi.w;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) tc_linear_fwd_kernel(const TcDev p) {
+__global__ void __launch_bounds__(kTcThreads, 3) tc_linear_fwd_kernel(const TcDev p) {
+  // Three CTAs per SM (68 KB smem, 128 TMEM columns each): while one CTA's MMAs or epilogue
+  // run, the others load -- the overlap a deeper ring would give, without the shared memory.
   extern __shared__ __align__(128) float smem[];
-  float* stage0 = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kTcStageFloats);  // [2] stage free
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  float* a_hi = smem;
+  float* a_lo = a_hi + kTcPlane;
+  float* b_hi = a_lo + kTcPlane;
+  float* b_lo = b_hi + kTcPlane;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kTcBufFloats);  // stage consumed by the MMAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * kTcM, col0 = blockIdx.y * kTcN;
   const int K = p.K;
@@ -116,8 +127,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_fwd_kernel(const TcDe
   const bool vw = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0);
 
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
   }
   if (warp == 0) {
@@ -131,48 +141,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_fwd_kernel(const TcDe
   const uint32_t tmem_d = *tmem_slot;
   const uint32_t idesc = umma_idesc_tf32(kTcM, kTcN);
 
-  for (int c = 0; c < nchunks; ++c) {
-    const int st = c & 1;
-    float* a_hi = stage0 + st * kTcStageFloats;
-    float* a_lo = a_hi + kTcPlane;
-    float* b_hi = a_lo + kTcPlane;
-    float* b_lo = b_hi + kTcPlane;
-    // the MMAs that read this stage two chunks ago must have completed
-    if (c >= 2) mbar_wait(&bars[st], ((c >> 1) - 1) & 1);
+  // thread -> pieces (row = idx / 8, quad = idx % 8), idx = tid + it*256: a warp reads 4 rows x
+  // 128 contiguous bytes of global memory and stores them to the [k quad][row][4] layout whose
+  // quad stride is padded by 16 B, so the 32 pieces of a warp spread evenly over the banks
+  // (4 wavefronts for 512 B: optimal).
+  float4 ra[kTcIters], rb[kTcIters];
+  auto load_regs = [&](int c) {
     const int k0 = c * kTcKC;
-    // 128 rows x 8 quads per operand; thread -> (row = idx / 8, quad = idx % 8): a warp reads
-    // 4 rows x 128 B of global memory per instruction
-    for (int idx = tid; idx < kTcM * (kTcKC / 4); idx += kTcThreads) {
+#pragma unroll
+    for (int it = 0; it < kTcIters; ++it) {
+      const int idx = tid + it * kTcThreads;
       const int r = idx >> 3, q = idx & 7;
       const int k = k0 + 4 * q;
       float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = make_float4(0.f, 0.f, 0.f, 0.f);
       const int row = row0 + r, col = col0 + r;
       if (row < p.batch) {
-        const float* s = p.in + (size_t)row * K;
-        if (vin && k + 3 < K) va = __ldg(reinterpret_cast<const float4*>(s + k));
+        const float* sp = p.in + (size_t)row * K;
+        if (vin && k + 3 < K) va = __ldg(reinterpret_cast<const float4*>(sp + k));
         else {
-          if (k < K) va.x = s[k];
-          if (k + 1 < K) va.y = s[k + 1];
-          if (k + 2 < K) va.z = s[k + 2];
-          if (k + 3 < K) va.w = s[k + 3];
+          if (k < K) va.x = sp[k];
+          if (k + 1 < K) va.y = sp[k + 1];
+          if (k + 2 < K) va.z = sp[k + 2];
+          if (k + 3 < K) va.w = sp[k + 3];
         }
       }
       if (col < p.N) {
-        const float* s = p.W + (size_t)col * K;
-        if (vw && k + 3 < K) vb = __ldg(reinterpret_cast<const float4*>(s + k));
+        const float* sp = p.W + (size_t)col * K;
+        if (vw && k + 3 < K) vb = __ldg(reinterpret_cast<const float4*>(sp + k));
         else {
-          if (k < K) vb.x = s[k];
-          if (k + 1 < K) vb.y = s[k + 1];
-          if (k + 2 < K) vb.z = s[k + 2];
-          if (k + 3 < K) vb.w = s[k + 3];
+          if (k < K) vb.x = sp[k];
+          if (k + 1 < K) vb.y = sp[k + 1];
+          if (k + 2 < K) vb.z = sp[k + 2];
+          if (k + 3 < K) vb.w = sp[k + 3];
         }
       }
+      ra[it] = va;
+      rb[it] = vb;
+    }
+  };
+
+  load_regs(0);
+  for (int c = 0; c < nchunks; ++c) {
+    // the MMAs of the previous chunk must have consumed the stage
+    if (c > 0) mbar_wait(bar, (c - 1) & 1);
+#pragma unroll
+    for (int it = 0; it < kTcIters; ++it) {
+      const int idx = tid + it * kTcThreads;
+      const int r = idx >> 3, q = idx & 7;
+      const int off = q * kTcQuadStride + r * 4;  // [k quad][row][4], padded quad stride
       float4 h, l;
-      const int off = q * (kTcM * 4) + r * 4;  // [k quad][row][4]
-      split4(va, h, l);
+      split4(ra[it], h, l);
       *reinterpret_cast<float4*>(a_hi + off) = h;
       *reinterpret_cast<float4*>(a_lo + off) = l;
-      split4(vb, h, l);
+      split4(rb[it], h, l);
       *reinterpret_cast<float4*>(b_hi + off) = h;
       *reinterpret_cast<float4*>(b_lo + off) = l;
     }
@@ -181,37 +202,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_fwd_kernel(const TcDe
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
-      constexpr uint32_t LBO = kTcM * 16;  // bytes between the two 16 B k-slices of one MMA
+      constexpr uint32_t LBO = kTcQuadStride * 4;  // bytes between the two 16 B k-slices of an MMA
       constexpr uint32_t SBO = 128;        // bytes between 8-row groups
 #pragma unroll
-      for (int s = 0; s < kTcKC / 8; ++s) {
-        const uint32_t koff = (uint32_t)(2 * s) * LBO;  // k quad 2s
+      for (int s4 = 0; s4 < kTcKC / 8; ++s4) {
+        const uint32_t koff = (uint32_t)(2 * s4) * LBO;  // k quad 2*s4
         const uint64_t dah = umma_desc(smem_u32(a_hi) + koff, LBO, SBO);
         const uint64_t dal = umma_desc(smem_u32(a_lo) + koff, LBO, SBO);
         const uint64_t dbh = umma_desc(smem_u32(b_hi) + koff, LBO, SBO);
         const uint64_t dbl = umma_desc(smem_u32(b_lo) + koff, LBO, SBO);
-        umma_tf32(tmem_d, dal, dbh, idesc, (c > 0 || s > 0) ? 1u : 0u);
+        umma_tf32(tmem_d, dal, dbh, idesc, (c > 0 || s4 > 0) ? 1u : 0u);
         umma_tf32(tmem_d, dah, dbl, idesc, 1u);
         umma_tf32(tmem_d, dah, dbh, idesc, 1u);
       }
-      umma_commit(&bars[st]);
+      umma_commit(bar);
     }
-    // no barrier here: the next chunk writes the other stage; its own mbarrier protects it
+    // global loads of the next chunk fly while the tensor core works on this one
+    if (c + 1 < nchunks) load_regs(c + 1);
   }
-  // wait for the last commit (covers all earlier MMAs of this thread as well)
-  {
-    const int last = nchunks - 1;
-    mbar_wait(&bars[last & 1], (last >> 1) & 1);
-  }
+  mbar_wait(bar, (nchunks - 1) & 1);
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
 
-  // ---- epilogue: TMEM -> registers -> bias + activation -> global ----
+  // ---- epilogue: TMEM -> registers -> bias + activation -> smem tile -> coalesced global ----
   // warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); warps 0-3 take columns [0,64),
-  // warps 4-7 columns [64,128)
+  // warps 4-7 columns [64,128).  The staging ring is free (all MMAs completed).
   {
+    constexpr int LDO = kTcLdo;    // padded row stride of the output tile in smem
+    float* otile = smem;           // 128 x 132 floats, reuses the operand stage
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
-    const int row = row0 + r;
     for (int cb = (warp >> 2) * 64; cb < (warp >> 2) * 64 + 64; cb += 32) {
       uint32_t v[32];
       const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)cb;
@@ -226,16 +245,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_fwd_kernel(const TcDe
             "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::);
-      if (row < p.batch) {
-        float* orow = p.out + (size_t)row * p.N;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + cb + j;
-          if (col < p.N) {
-            const float bias = p.b ? __ldg(p.b + col) : 0.f;
-            orow[col] = act_fwd(__uint_as_float(v[j]) + bias, p.act);
-          }
-        }
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(otile + r * LDO + cb + j) =
+            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                        __uint_as_float(v[j + 3]));
+    }
+    __syncthreads();
+    // each warp writes whole 512-byte row segments; bias + activation applied on the way out
+    const bool vo = ((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    for (int idx = tid; idx < kTcM * (kTcN / 4); idx += kTcThreads) {
+      const int rr = idx >> 5, c4 = (idx & 31) * 4;
+      const int row = row0 + rr, col = col0 + c4;
+      if (row >= p.batch || col >= p.N) continue;
+      float4 o = *reinterpret_cast<const float4*>(otile + rr * LDO + c4);
+      float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (col + j < p.N) ov[j] = act_fwd(ov[j] + (p.b ? __ldg(p.b + col + j) : 0.f), p.act);
+      float* dst = p.out + (size_t)row * p.N + col;
+      if (vo && col + 3 < p.N) {
+        *reinterpret_cast<float4*>(dst) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (col + j < p.N) dst[j] = ov[j];
       }
     }
   }
