@@ -149,6 +149,27 @@ int rb200_num_row_tiles(int batch, int max_dim_in, int max_dim_hidden);
 int rb200_dqn_td_step(const rb200_mlp_t* q_net, const rb200_mlp_t* q_target,
                       const rb200_dqn_args_t* args, const rb200_net_ws_t* ws, void* stream);
 
+/* The same step on the 5th-generation tensor cores (tcgen05.mma kind::tf32 with 3xTF32 error
+ * compensation, accumulators in Tensor Memory, weights streamed by bulk async copies):
+ * rb200_dqn_tc.cu.  Same arguments, semantics and reference lines as rb200_dqn_td_step plus a
+ * caller-owned scratch buffer for the packed hi/lo weight images (re-packed on every call,
+ * because the weights change on every update).
+ *   rb200_dqn_tc_workspace_bytes: bytes the scratch buffer needs for this network, or 0 when
+ *       the shapes do not fit the tensor-core path (then use rb200_dqn_td_step).
+ *   rb200_dqn_tc_pack: (re)build the hi/lo weight images from the current parameters.  It only
+ *       depends on the parameters, so a caller may run it on a side stream as soon as the
+ *       previous optimizer step is done (e.g. concurrently with replay sampling) and pass
+ *       weights_packed = 1; with weights_packed = 0 the step packs first, on `stream`.
+ *       The images depend on (double_q, do_backward) only through which ones are built.
+ *   pack_ws: device buffer, 128-byte aligned, zero-initialised ONCE by the caller. */
+int64_t rb200_dqn_tc_workspace_bytes(const rb200_mlp_t* q_net, int32_t double_q,
+                                     int32_t do_backward);
+int rb200_dqn_tc_pack(const rb200_mlp_t* q_net, const rb200_mlp_t* q_target, int32_t double_q,
+                      int32_t do_backward, void* pack_ws, int64_t pack_ws_bytes, void* stream);
+int rb200_dqn_td_step_tc(const rb200_mlp_t* q_net, const rb200_mlp_t* q_target,
+                         const rb200_dqn_args_t* args, const rb200_net_ws_t* ws, void* pack_ws,
+                         int64_t pack_ws_bytes, int32_t weights_packed, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* QR-DQN (reagent/training/qrdqn_trainer.py:108-194).  The [hidden -> A*N] head  */
 /* is too wide for a row tile, so it runs as 2-D tiled launches:                   */

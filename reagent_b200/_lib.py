@@ -162,7 +162,10 @@ class Rb200Error(RuntimeError):
 
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libreagent_b200.so")
+# RB200_LIB selects another build of the SAME library (e.g. the profiling build with the
+# clock64 timeline compiled in); there is no other implementation to fall back to.
+LIB_PATH = os.environ.get("RB200_LIB") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "libreagent_b200.so")
 
 
 def _declare(lib):
@@ -172,6 +175,12 @@ def _declare(lib):
     lib.rb200_num_row_tiles.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.rb200_dqn_td_step.argtypes = [C.POINTER(MlpT), C.POINTER(MlpT), C.POINTER(DqnArgsT),
                                       C.POINTER(NetWsT), _vp]
+    lib.rb200_dqn_tc_workspace_bytes.argtypes = [C.POINTER(MlpT), C.c_int32, C.c_int32]
+    lib.rb200_dqn_tc_workspace_bytes.restype = C.c_int64
+    lib.rb200_dqn_tc_pack.argtypes = [C.POINTER(MlpT), C.POINTER(MlpT), C.c_int32, C.c_int32, _vp,
+                                      C.c_int64, _vp]
+    lib.rb200_dqn_td_step_tc.argtypes = [C.POINTER(MlpT), C.POINTER(MlpT), C.POINTER(DqnArgsT),
+                                         C.POINTER(NetWsT), _vp, C.c_int64, C.c_int32, _vp]
     lib.rb200_mlp_forward.argtypes = [C.POINTER(MlpT), _vp, C.c_int32, _vp, C.c_int32, C.c_int32,
                                       _vp, C.POINTER(NetWsT), _vp]
     lib.rb200_linear_forward.argtypes = [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp,

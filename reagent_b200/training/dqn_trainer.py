@@ -8,6 +8,8 @@
 from dataclasses import dataclass
 from typing import List, Optional
 
+import os
+
 import torch
 
 from .. import _lib
@@ -105,6 +107,41 @@ class DQNTrainer(DQNTrainerBaseLightning):
             self._ws = ws
         return ws
 
+    _tc_prepacked = False  # set by a caller that already ran rb200_dqn_tc_pack (fused_step.py)
+
+    def _tc_pack(self, qd, a, device):
+        """Scratch for the tcgen05 path of K2 (packed hi/lo weight images), or None when the
+        network does not fit it (or RB200_DISABLE_TCGEN05 is set): then the mma.sync row-tile
+        kernel runs.  Both are this library's CUDA kernels; there is no other fallback."""
+        return self._tc_pack_for((int(a.double_q), int(a.do_backward)), qd, device)
+
+    def _tc_pack_for(self, key, qd, device):
+        cache = self.__dict__.setdefault("_tc_pack_cache", {})
+        pack = cache.get(key, False)
+        if pack is False or (pack is not None and pack.device != device):
+            nbytes = 0
+            if not os.environ.get("RB200_DISABLE_TCGEN05"):
+                nbytes = int(_lib.lib().rb200_dqn_tc_workspace_bytes(qd, key[0], key[1]))
+            pack = torch.zeros(nbytes, dtype=torch.uint8, device=device) if nbytes > 0 else None
+            cache[key] = pack
+        return pack
+
+    def tc_prepack(self) -> bool:
+        """Build the weight images of the tcgen05 K2 on the CURRENT stream, for the next
+        training `_td_step` (which then skips the packing).  The images depend only on the
+        parameters, so a caller may run this on a side stream next to the replay sampling
+        (fused_step.py).  Returns False when K2 runs on the row-tile kernel instead."""
+        qd, qtd = self.q_network.arena.desc(), self.q_network_target.arena.desc()
+        key = (int(bool(self.double_q_learning)), 1)
+        pack = self._tc_pack_for(key, qd, self.q_network.arena.flat.device)
+        if pack is None:
+            return False
+        rc = _lib.lib().rb200_dqn_tc_pack(qd, qtd, key[0], key[1], pack.data_ptr(), pack.numel(),
+                                          _lib.cur_stream())
+        _lib.check(rc, "rb200_dqn_tc_pack")
+        self._tc_prepacked = True
+        return True
+
     def _td_step(self, batch: rlt.DiscreteDqnInput, do_backward: bool = True) -> torch.Tensor:
         """Fused TD target + loss (+ backward).  Returns the device loss scalar (shape [])."""
         state = _f32c(batch.state.float_features)
@@ -157,9 +194,19 @@ class DQNTrainer(DQNTrainerBaseLightning):
         if ev is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        rc = _lib.lib().rb200_dqn_td_step(qd, qtd, a, ws["net"].c, _lib.cur_stream())
-        _lib.check(rc, "rb200_dqn_td_step")
-        self._last_td_call = (qd, qtd, a, ws["net"].c, keep)  # profiling hook (re-launch)
+        pack = self._tc_pack(qd, a, state.device)
+        if pack is not None:
+            rc = _lib.lib().rb200_dqn_td_step_tc(qd, qtd, a, ws["net"].c, pack.data_ptr(),
+                                                 pack.numel(),
+                                                 int(self._tc_prepacked and do_backward),
+                                                 _lib.cur_stream())
+            if do_backward:
+                self._tc_prepacked = False
+            _lib.check(rc, "rb200_dqn_td_step_tc")
+        else:
+            rc = _lib.lib().rb200_dqn_td_step(qd, qtd, a, ws["net"].c, _lib.cur_stream())
+            _lib.check(rc, "rb200_dqn_td_step")
+        self._last_td_call = (qd, qtd, a, ws["net"].c, keep, pack)  # profiling hook (re-launch)
         if ev is not None:
             e1.record()
             ev.append((e0, e1))

@@ -30,6 +30,7 @@ class FusedDqnStep:
         self.slots = []
         self.k = 0
         self.h2d_bytes = batch_size * 8
+        self._side = torch.cuda.Stream(device=self.dev)
         self.d2h_bytes = 4
         replay_buffer._flush()
         # warm-up outside capture (lazy allocations, cudaFuncSetAttribute, optimizer state)
@@ -40,13 +41,29 @@ class FusedDqnStep:
 
     # -- one update on the current stream ---------------------------------------
     def _one_update(self, rnd_dev):
+        # the tcgen05 K2 wants hi/lo weight images: they only depend on the parameters, so they
+        # are built on a side stream while the replay-sample kernel runs (fork/join is
+        # captured into the graph like any other dependency)
+        main = torch.cuda.current_stream()
+        prepack = getattr(self.trainer, "tc_prepack", None)
+        forked = False
+        if prepack is not None:
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                forked = prepack()
+        batch = self._sample(rnd_dev)
+        if forked:
+            main.wait_stream(self._side)
+        return self.trainer.train_batch(batch, process_group=self.pg)
+
+    def _sample(self, rnd_dev):
         if rnd_dev is None:
             batch = self.rb.sample_discrete_dqn_batch(self.B, self.A)
         elif self.prioritized:
             batch = self.rb.sample_discrete_dqn_batch(self.B, self.A, query_dev=rnd_dev)
         else:
             batch = self.rb.sample_discrete_dqn_batch(self.B, self.A, ranks_dev=rnd_dev)
-        return self.trainer.train_batch(batch, process_group=self.pg)
+        return batch
 
     def _capture(self):
         dt = torch.float64 if self.prioritized else torch.int64

@@ -9,6 +9,21 @@ from tests.test_oracle_golden import DQN_CASES, _dqn_kwargs
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
+# K2 has two implementations in the library: tcgen05 (rb200_dqn_tc.cu, preferred when the
+# shapes fit) and the mma.sync row-tile kernel (rb200_dqn.cu); every golden case runs on both.
+K2_PATHS = ["tcgen05", "rows"]
+
+
+def _select_k2(monkeypatch, path):
+    if path == "rows":
+        monkeypatch.setenv("RB200_DISABLE_TCGEN05", "1")
+    else:
+        monkeypatch.delenv("RB200_DISABLE_TCGEN05", raising=False)
+
+
+def _assert_k2(t, path):
+    used_tc = t._last_td_call[-1] is not None
+    assert used_tc == (path == "tcgen05"), f"K2 ran on the wrong kernel (wanted {path})"
 
 
 def _build_trainer(meta, arrays=None, dev="cuda"):
@@ -61,10 +76,12 @@ def _check_against_golden(t, arrays, meta, losses):
         assert G.rel_err(seq[0].bias, arrays[f"qtN.b{i}"]) < TOL
 
 
+@pytest.mark.parametrize("path", K2_PATHS)
 @pytest.mark.parametrize("name", DQN_CASES)
-def test_dqn_generator_path_matches_reference(name):
+def test_dqn_generator_path_matches_reference(name, path, monkeypatch):
     from reagent_b200.training import run_update
 
+    _select_k2(monkeypatch, path)
     arrays, meta = G.load(name)
     t = _build_trainer(meta, arrays)
     batch = _rlt_batch(G.batch_tensors(arrays, "cuda"), meta)
@@ -88,20 +105,26 @@ def test_dqn_generator_path_matches_reference(name):
             gen_losses = run_update(t, batch, it)
             assert len(gen_losses) == 2
             losses.append(float(gen_losses[0]))
+    _assert_k2(t, path)
     _check_against_golden(t, arrays, meta, losses)
 
 
+@pytest.mark.parametrize("path", K2_PATHS)
 @pytest.mark.parametrize("name", DQN_CASES)
-def test_dqn_fast_path_matches_reference(name):
+def test_dqn_fast_path_matches_reference(name, path, monkeypatch):
+    _select_k2(monkeypatch, path)
     arrays, meta = G.load(name)
     t = _build_trainer(meta, arrays)
     batch = _rlt_batch(G.batch_tensors(arrays, "cuda"), meta)
     losses = [float(t.train_batch(batch, it)) for it in range(meta["n_updates"])]
+    _assert_k2(t, path)
     _check_against_golden(t, arrays, meta, losses)
 
 
-def test_dqn_config2_matches_oracle():
+@pytest.mark.parametrize("path", K2_PATHS)
+def test_dqn_config2_matches_oracle(path, monkeypatch):
     """BASELINE config 2 shapes: S=128, A=16, B=4096, [256,128] relu, double-Q, huber."""
+    _select_k2(monkeypatch, path)
     meta = dict(S=128, A=16, B=4096, sizes=[256, 128], acts=["relu", "relu"], gamma=0.99,
                 tau=0.005, loss="huber", maxq=True, multi_steps=None, time_diff=False,
                 boost=None, double_q=True, lr=1e-3, n_updates=3)
@@ -131,6 +154,7 @@ def test_dqn_config2_matches_oracle():
         lo, grads, aux = O.dqn_update(qo, qt, adam, b, gamma=meta["gamma"], tau=meta["tau"],
                                       double_q=True, maxq=True, loss="huber")
         t._td_step(batch)
+        _assert_k2(t, path)
         if it == 0:
             assert torch.equal(t._ws["next_idx"].cpu().long(), aux["next_idx"].reshape(-1))
             assert G.rel_err(t._ws["td_target"], aux["target"].reshape(-1)) < TOL
@@ -171,3 +195,71 @@ def test_mlp_forward_matches_torch():
         ref = seq(ref)
     out = c.cuda()(rlt.FeatureData(s.cuda()), rlt.FeatureData(a.cuda()))
     assert G.rel_err(out, ref) < TOL
+
+
+@pytest.mark.parametrize("B,S,sizes,A,acts,loss,double_q,maxq", [
+    (4096, 128, [256, 128], 16, ["relu", "relu"], "huber", True, True),   # BASELINE config 2
+    (100, 10, [24, 12], 3, ["tanh", "relu"], "mse", False, True),         # ragged rows, odd dims
+    (33, 7, [40], 5, ["leaky_relu"], "huber", True, False),               # SARSA, one hidden layer
+    (257, 36, [300, 130, 20], 9, ["relu", "sigmoid", "relu"], "mse", True, True),  # >128-wide tiles
+])
+def test_k2_tcgen05_matches_rows_kernel(B, S, sizes, A, acts, loss, double_q, maxq):
+    """The two K2 kernels on identical inputs: every output (loss, scores, TD target, arg max,
+    saved activations, dZ of every layer) within 1e-5 of the tensor's scale; arg max bit-exact."""
+    from reagent_b200 import _lib
+
+    meta = dict(S=S, A=A, B=B, sizes=sizes, acts=acts, gamma=0.97, tau=0.01, loss=loss,
+                maxq=maxq, multi_steps=None, time_diff=False, boost=None, double_q=double_q,
+                lr=1e-3, n_updates=1)
+    torch.manual_seed(B + S)
+    t = _build_trainer(meta)
+    with torch.no_grad():
+        for p_ in t.q_network_target.parameters():
+            p_.add_(0.05 * torch.randn_like(p_))
+    act = torch.randint(A, (B,))
+    nact = torch.randint(A, (B,))
+    nt = (torch.rand(B, 1) > 0.1).float()
+    mask = (torch.rand(B, A) > 0.3).float()
+    mask[torch.arange(B), nact] = 1.0
+    b = dict(state=torch.randn(B, S), next_state=torch.randn(B, S), reward=torch.randn(B, 1),
+             time_diff=torch.ones(B, 1), step=None, not_terminal=nt,
+             action=torch.nn.functional.one_hot(act, A).float(),
+             next_action=torch.nn.functional.one_hot(nact, A).float() * nt,
+             possible_actions_mask=torch.ones(B, A), possible_next_actions_mask=mask)
+    batch = _rlt_batch({k: (v.cuda() if v is not None else None) for k, v in b.items()}, meta)
+    t._td_step(batch)
+    qd, qtd, a, wsc, keep, pack = t._last_td_call
+    assert pack is not None, "shapes expected to fit the tcgen05 path"
+    ws, st = t._ws, _lib.cur_stream()
+
+    def run(tc):
+        for x in ws["net"].hidden + ws["net"].dz:
+            x.zero_()
+        if tc:
+            rc = _lib.lib().rb200_dqn_td_step_tc(qd, qtd, a, wsc, pack.data_ptr(), pack.numel(), 0, st)
+        else:
+            rc = _lib.lib().rb200_dqn_td_step(qd, qtd, a, wsc, st)
+        _lib.check(rc, "k2")
+        torch.cuda.synchronize()
+        out = {"loss": ws["loss"].clone(), "scores": ws["scores"].clone(),
+               "tgt": ws["td_target"].clone(), "qsel": ws["q_sel"].clone(), "idx": ws["next_idx"].clone()}
+        out.update({f"h{i}": h.clone() for i, h in enumerate(ws["net"].hidden)})
+        out.update({f"dz{i}": z.clone() for i, z in enumerate(ws["net"].dz)})
+        return out
+
+    r_rows, r_tc = run(False), run(True)
+    assert torch.equal(r_rows["idx"], r_tc["idx"])
+    for k in r_rows:
+        if k == "idx":
+            continue
+        x, y = r_rows[k].double(), r_tc[k].double()
+        scale = max(float(x.abs().max()), 1e-30)
+        if k.startswith("dz") and x.numel() > 100000:
+            # a hidden unit whose pre-activation is within fp32 noise of 0 may get the other
+            # ReLU mask in the two kernels (see golden_util.grad_close) and the flip spreads
+            # over that row of the upstream dZ: bound the relative L2 error instead
+            # (measured 1.4e-6) -- the small shapes below stay element-wise strict
+            l2 = float((x - y).norm() / (x.norm() + 1e-30))
+            assert l2 < 1e-4, (k, l2)
+            continue
+        assert float((x - y).abs().max()) <= TOL * scale, (k, float((x - y).abs().max()), scale)
