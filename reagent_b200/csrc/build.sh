@@ -22,7 +22,7 @@ for p in $pids; do wait $p; done
 cobjs=""
 for s in $(ls rb200_*.c 2>/dev/null); do
   o=build/${s%.c}.o
-  gcc -O2 -fPIC -std=c11 -c "$s" -o "$o"
+  gcc -O3 -fPIC -std=c11 -c "$s" -o "$o"
   cobjs="$cobjs $o"
 done
 $NVCC -shared -o $OUT $objs $cobjs -lcudart

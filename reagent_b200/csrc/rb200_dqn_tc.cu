@@ -52,6 +52,7 @@ constexpr int kQLoOff = 32 * 4;                           // floats from a hi el
 constexpr int kQEpiThreads = 256;
 constexpr int kQThreads = kQEpiThreads + 64;              // + producer warp + MMA warp
 constexpr int kQTmemCols = 256;                           // 4 feature tiles x 64 columns
+constexpr int kQMaxTiles = kQTmemCols / 64;
 constexpr int kQMaxSteps = 4 * kMaxLayers;
 constexpr int kQMaxSmem = 232448;
 #ifndef RB200_TC_TIMELINE
@@ -212,7 +213,10 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t t0, uint32_t t1, uint32_t (
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-__global__ void __launch_bounds__(kQThreads, 1)
+// 160 registers x 320 threads and ~214 KB of shared memory leave room on the SM for one CTA
+// of the replay-sample kernel (48 registers x 256 threads, < 10 KB), so the sampler of the next
+// update can run on a second stream underneath this kernel instead of delaying its CTAs.
+__global__ void __maxnreg__(160)
 dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -243,14 +247,14 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
   float* scal_s = mask_s + kQR * A;                               // [kQR][4] reward, not_terminal, discount src
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + p.bar_off);
   uint64_t* done = full + kQStages;
-  uint64_t* dready = done + kQStages;
-  uint64_t* opready = dready + 1;
+  uint64_t* dready = done + kQStages;  // one per accumulator tile (see the epilogue)
+  uint64_t* opready = dready + kQMaxTiles;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(opready + 1);
   const int ldq = p.ldq;
 
   if (tid == 0) {
     for (int s = 0; s < kQStages; ++s) { mbar_init(full + s, 1); mbar_init(done + s, 1); }
-    mbar_init(dready, 1);
+    for (int t = 0; t < kQMaxTiles; ++t) mbar_init(dready + t, 1);
     mbar_init(opready, kQEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -347,7 +351,7 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
           if (++stage == kQStages) { stage = 0; par ^= 1u; }
         }
         // one accumulator tile complete: its epilogue runs while the next tile's MMAs issue
-        if (leader) umma_commit(dready);
+        if (leader) umma_commit(dready + t);
       }
       if (leader) {
         if (kTimeline && p.dbg && blockIdx.x == 0) { p.dbg[s * 8 + 1] = clock64(); p.dbg[s * 8 + 2] = wfull; p.dbg[s * 8 + 6] = wissue; p.dbg[s * 8 + 7] = wcommit; }
@@ -357,7 +361,7 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
   } else {
     // =====================  operand producers / epilogue warps  =====================
     const int quad = warp & 3, grp = warp >> 2;
-    uint32_t dphase = 0;       // accumulator tiles consumed so far (phase of `dready`)
+    uint32_t dphase = 0;       // bit t: parity of the next phase of dready[t]
 
     // The input tile of a pass: global -> registers (x_fetch, issued early so that the load
     // latency hides behind the previous layer) -> hi/lo split -> B operand (x_store).
@@ -434,8 +438,13 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
       const int mt = ceil_div(N, 128);
       float* obase = reinterpret_cast<float*>(smem_raw + p.buf_off[st.out_buf]);
       for (int t = 0; t < mt; ++t) {
-        mbar_wait(dready, dphase & 1u);
-        ++dphase;
+        // One barrier per tile: the MMA warp runs ahead through the tiles of a step without
+        // waiting for the epilogues, so a shared barrier could complete two phases before a
+        // slow thread looks at it (and parity waits cannot tell "two ahead" from "not yet").
+        // Per tile there is at most one completion per step, and steps are serialised by
+        // `opready`.
+        mbar_wait(dready + t, (dphase >> t) & 1u);
+        dphase ^= 1u << t;
         tc_fence_after();
         const int h16 = grp * 16;
         const int n = t * 128 + quad * 32 + lane;
@@ -453,13 +462,27 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
           // act'(h_{l-1}) from the forward operand still resident in shared memory (h = hi + lo
           // exactly); dZ_{l-1} then replaces it in place as the next B operand
           const int hact = q.act[l - 1];
+          // st.save: the shared-memory copy of h_{l-1} was overwritten by a later forward layer
+          // (networks with >= 3 hidden layers ping-pong over the same two buffers); read the
+          // copy saved for the weight-gradient kernel instead
+          float hv[16];
+          if (st.save) {
+            const float* hs = p.ws.hidden[l - 1];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int row = row0 + h16 + j;
+              hv[j] = (valid && row < B) ? hs[(size_t)row * N + n] : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) hv[j] = valid ? ob[j * 4] + ob[j * 4 + kQLoOff] : 0.f;
+          }
           if (hact == RB200_ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] = (valid && ob[j * 4] > 0.f) ? x[j] : 0.f;
+            for (int j = 0; j < 16; ++j) x[j] = hv[j] > 0.f ? x[j] : 0.f;
           } else if (hact != RB200_ACT_LINEAR) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              x[j] = valid ? x[j] * act_bwd_slow(ob[j * 4] + ob[j * 4 + kQLoOff], hact) : 0.f;
+            for (int j = 0; j < 16; ++j) x[j] = valid ? x[j] * act_bwd_slow(hv[j], hact) : 0.f;
           }
           to_operand = l - 1 >= 1;
           to_global = true;
@@ -655,7 +678,7 @@ static QPlan make_plan(const rb200_mlp_t* qn, const rb200_mlp_t* qtn, int double
   const int L = qn->n_layers;
   if (L < 1 || L > kMaxLayers) return pl;
   for (int l = 1; l <= L; ++l)
-    if (qn->dims[l] > 128 * (kQTmemCols / 64) || qn->dims[l] > 32000) return pl;
+    if (qn->dims[l] > 128 * kQMaxTiles || qn->dims[l] > 32000) return pl;
   if (qn->dims[0] > 32000 || qn->dims[L] > 256) return pl;
 
   // weight images: online fwd, target fwd, online bwd (transposed)
@@ -720,6 +743,7 @@ static QPlan make_plan(const rb200_mlp_t* qn, const rb200_mlp_t* qtn, int double
       // overwrites h_{l-1} in place
       s.in_buf = (int8_t)(l == L - 1 ? 2 : ((l + 1) & 1));
       s.out_buf = (int8_t)(l & 1);
+      s.save = (int8_t)(l <= L - 3 ? 1 : 0);  // h_{l-1} clobbered by h_{l+1}: use the global copy
     }
   }
   pl.dev.nsteps = ns;
@@ -740,7 +764,7 @@ static QPlan make_plan(const rb200_mlp_t* qn, const rb200_mlp_t* qtn, int double
   o += ((size_t)2 * kQR * qn->dims[L] + 4 * kQR + 8) * sizeof(float);
   o = (o + 15) & ~(size_t)15;
   pl.dev.bar_off = (int)o;
-  o += (2 * kQStages + 2) * sizeof(uint64_t) + 16;
+  o += (2 * kQStages + kQMaxTiles + 1) * sizeof(uint64_t) + 16;
   pl.smem_bytes = (o + 15) & ~(size_t)15;
   pl.ok = pl.smem_bytes <= (size_t)kQMaxSmem;
   return pl;

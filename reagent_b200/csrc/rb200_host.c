@@ -14,38 +14,61 @@
 #define MT_N 624
 #define MT_M 397
 
-static uint32_t mt_next(uint32_t* mt, int32_t* index) {
-  static const uint32_t mag01[2] = {0x0U, 0x9908b0dfU};
-  uint32_t y;
-  if (*index >= MT_N) {
-    int kk;
-    for (kk = 0; kk < MT_N - MT_M; kk++) {
-      y = (mt[kk] & 0x80000000U) | (mt[kk + 1] & 0x7fffffffU);
-      mt[kk] = mt[kk + MT_M] ^ (y >> 1) ^ mag01[y & 0x1U];
-    }
-    for (; kk < MT_N - 1; kk++) {
-      y = (mt[kk] & 0x80000000U) | (mt[kk + 1] & 0x7fffffffU);
-      mt[kk] = mt[kk + (MT_M - MT_N)] ^ (y >> 1) ^ mag01[y & 0x1U];
-    }
-    y = (mt[MT_N - 1] & 0x80000000U) | (mt[0] & 0x7fffffffU);
-    mt[MT_N - 1] = mt[MT_M - 1] ^ (y >> 1) ^ mag01[y & 0x1U];
-    *index = 0;
+/* state regeneration ("twist"): three branch-free loops whose reads run ahead of their writes,
+ * so the compiler can vectorise them */
+static void mt_twist(uint32_t* mt) {
+  int kk;
+  for (kk = 0; kk < MT_N - MT_M; kk++) {
+    const uint32_t y = (mt[kk] & 0x80000000U) | (mt[kk + 1] & 0x7fffffffU);
+    mt[kk] = mt[kk + MT_M] ^ (y >> 1) ^ ((uint32_t)(-(int32_t)(y & 0x1U)) & 0x9908b0dfU);
   }
-  y = mt[(*index)++];
-  y ^= (y >> 11);
-  y ^= (y << 7) & 0x9d2c5680U;
-  y ^= (y << 15) & 0xefc60000U;
-  y ^= (y >> 18);
-  return y;
+  for (; kk < MT_N - 1; kk++) {
+    const uint32_t y = (mt[kk] & 0x80000000U) | (mt[kk + 1] & 0x7fffffffU);
+    mt[kk] = mt[kk + (MT_M - MT_N)] ^ (y >> 1) ^ ((uint32_t)(-(int32_t)(y & 0x1U)) & 0x9908b0dfU);
+  }
+  {
+    const uint32_t y = (mt[MT_N - 1] & 0x80000000U) | (mt[0] & 0x7fffffffU);
+    mt[MT_N - 1] = mt[MT_M - 1] ^ (y >> 1) ^ ((uint32_t)(-(int32_t)(y & 0x1U)) & 0x9908b0dfU);
+  }
+}
+
+/* the next `count` tempered 32-bit outputs of the stream (genrand_uint32 x count) */
+static void mt_fill(uint32_t* mt, int32_t* index, uint32_t* dst, int64_t count) {
+  while (count > 0) {
+    if (*index >= MT_N) {
+      mt_twist(mt);
+      *index = 0;
+    }
+    int64_t take = MT_N - *index;
+    if (take > count) take = count;
+    const uint32_t* src = mt + *index;
+    for (int64_t i = 0; i < take; ++i) {
+      uint32_t y = src[i];
+      y ^= (y >> 11);
+      y ^= (y << 7) & 0x9d2c5680U;
+      y ^= (y << 15) & 0xefc60000U;
+      y ^= (y >> 18);
+      dst[i] = y;
+    }
+    dst += take;
+    count -= take;
+    *index += (int32_t)take;
+  }
 }
 
 void rb200_mt19937_uniform_host(uint32_t* state624, int32_t* index, const double* lo,
                                 const double* hi, double* out, int64_t n) {
-  for (int64_t i = 0; i < n; ++i) {
-    /* random(): 53-bit resolution double in [0,1) */
-    const uint32_t a = mt_next(state624, index) >> 5, b = mt_next(state624, index) >> 6;
-    const double r = (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
-    out[i] = (lo && hi) ? lo[i] + (hi[i] - lo[i]) * r : r;
+  enum { CHUNK = 1024 };
+  uint32_t raw[2 * CHUNK];
+  for (int64_t base = 0; base < n; base += CHUNK) {
+    const int64_t m = (n - base < CHUNK) ? n - base : CHUNK;
+    mt_fill(state624, index, raw, 2 * m);
+    for (int64_t i = 0; i < m; ++i) {
+      /* random(): 53-bit resolution double in [0,1) */
+      const uint32_t a = raw[2 * i] >> 5, b = raw[2 * i + 1] >> 6;
+      const double r = (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+      out[base + i] = (lo && hi) ? lo[base + i] + (hi[base + i] - lo[base + i]) * r : r;
+    }
   }
 }
 

@@ -20,7 +20,7 @@
 namespace rb200 {
 
 constexpr int kSPB = 32;  // samples per CTA
-constexpr int kTopLevels = 11;
+constexpr int kTopLevels = 10;  // 8 KB: small enough to share an SM with the tcgen05 TD kernel
 
 struct SampleDev {
   rb200_sample_args_t a;
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kThreads) replay_sample_kernel(const SampleDev
   __shared__ long long s_idx[kSPB];
   __shared__ long long s_next[kSPB];
   __shared__ int s_term[kSPB];
-  // top kTopLevels levels of the fp64 sum tree (2^kTopLevels - 1 nodes, 16 KB): loaded once
+  // top kTopLevels levels of the fp64 sum tree (2^kTopLevels - 1 nodes, 8 KB): loaded once
   // per CTA with coalesced reads so that only the deep levels cost a dependent L2 round trip
   __shared__ double s_top[(1 << kTopLevels) - 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

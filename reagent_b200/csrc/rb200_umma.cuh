@@ -60,7 +60,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (ok) break;
-    if (it > 50000000LL) __trap();  // never spin forever on a protocol bug
+    if (it > 400000LL) __trap();  // ~2 s (a failed try_wait blocks a few us): never spin forever on a protocol bug
   }
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

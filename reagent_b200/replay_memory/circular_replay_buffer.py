@@ -537,6 +537,35 @@ class ReplayBuffer:
         pass
 
     # ---------------------------------------------------- fused trainer batches
+    # ---- caller-owned output buffers for the fused trainer batches -----------------------
+    _out_pool = None
+
+    def output_buffers(self, pool: dict):
+        """Context manager: while active, the fused `sample_*_batch` calls write their outputs
+        into the tensors of `pool` (filled on first use) instead of fresh allocations, so a
+        captured sampling launch can feed another captured graph through fixed addresses
+        (training/fused_step.py, prefetch mode)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            prev, self._out_pool = self._out_pool, pool
+            try:
+                yield pool
+            finally:
+                self._out_pool = prev
+        return cm()
+
+    def _alloc(self, name, *shape, dtype=torch.float32):
+        pool = self._out_pool
+        if pool is None:
+            return torch.empty(*shape, dtype=dtype, device=self._dev())
+        t = pool.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(*shape, dtype=dtype, device=self._dev())
+            pool[name] = t
+        return t
+
     def _fused_common(self, batch_size, indices, index_kwargs):
         if self._stack_size != 1:
             raise NotImplementedError("fused trainer batches need stack_size == 1")
@@ -567,12 +596,12 @@ class ReplayBuffer:
             keep += [cols, quant]
         args.obs_out_dim = s_out
         t = {
-            "state": torch.empty(B, s_out, device=dev),
-            "next_state": torch.empty(B, s_out, device=dev),
-            "reward": torch.empty(B, 1, device=dev),
-            "not_terminal": torch.empty(B, 1, device=dev),
-            "step": torch.empty(B, 1, device=dev),
-            "indices": torch.empty(B, 1, dtype=torch.int64, device=dev),
+            "state": self._alloc("state", B, s_out),
+            "next_state": self._alloc("next_state", B, s_out),
+            "reward": self._alloc("reward", B, 1),
+            "not_terminal": self._alloc("not_terminal", B, 1),
+            "step": self._alloc("step", B, 1),
+            "indices": self._alloc("indices", B, 1, dtype=torch.int64),
         }
         args.state = t["state"].data_ptr()
         args.next_state = t["next_state"].data_ptr()
@@ -605,15 +634,15 @@ class ReplayBuffer:
             raise NotImplementedError("discrete batches need an int64 scalar action")
         args, t, keep = self._fused_common(batch_size, indices, index_kwargs)
         B, dev = batch_size, self._dev()
-        action = torch.empty(B, num_actions, device=dev)
-        next_action = torch.empty(B, num_actions, device=dev)
+        action = self._alloc("action", B, num_actions)
+        next_action = self._alloc("next_action", B, num_actions)
         args.action_i64 = self._store["action"].data_ptr()
         args.num_actions = num_actions
         args.action_onehot = action.data_ptr()
         args.next_action_onehot = next_action.data_ptr()
         prob = None
         if "log_prob" in self._store:
-            lp = torch.empty(B, 1, device=dev)
+            lp = self._alloc("log_prob", B, 1)
             args.n_specs = 1
             args.specs[0].src = self._store["log_prob"].data_ptr()
             args.specs[0].dst = lp.data_ptr()
@@ -647,8 +676,8 @@ class ReplayBuffer:
         lo = torch.as_tensor(np.asarray(action_low, dtype=np.float32)).reshape(-1).to(dev)
         hi = torch.as_tensor(np.asarray(action_high, dtype=np.float32)).reshape(-1).to(dev)
         keep += [lo, hi]
-        action = torch.empty(B, A, device=dev)
-        next_action = torch.empty(B, A, device=dev)
+        action = self._alloc("action", B, A)
+        next_action = self._alloc("next_action", B, A)
         args.action_f32 = self._store["action"].data_ptr()
         args.action_dim = A
         args.action_rescaled = action.data_ptr()

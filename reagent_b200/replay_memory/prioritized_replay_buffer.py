@@ -161,7 +161,7 @@ class PrioritizedReplayBuffer(circular_replay_buffer.ReplayBuffer):
         keep.append(heap)
         args.tree = heap.data_ptr()
         args.tree_depth = self.sum_tree.depth
-        out["sampling_probabilities"] = torch.empty(B, dtype=torch.float32, device=self._dev())
+        out["sampling_probabilities"] = self._alloc("sampling_probabilities", B)
         args.sampling_prob_out = out["sampling_probabilities"].data_ptr()
 
     def sample_transition_batch(self, batch_size=None, indices=None):

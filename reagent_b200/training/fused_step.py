@@ -6,7 +6,14 @@ replay_buffer_dataset.py:122-133 + reagent/training/reagent_lightning_module.py:
 per update the host only draws the random numbers (Python's `random` stream for the
 prioritized buffer, torch.randint for the uniform one -- bit-exact index parity with the
 reference), writes them to pinned memory and replays one captured graph that does the
-host->device copy, the 4 kernels and the device->host copy of the loss.
+host->device copy, the kernels and the device->host copy of the loss.
+
+`prefetch=True` pipelines the sampler one update ahead, the way the reference's DataLoader
+over ReplayBufferDataset prefetches batches: the graph of update k trains on the batch drawn
+during update k-1 while the replay-sample kernel for update k+1 runs on a second stream (it
+does not depend on the parameters).  The host's random stream is consumed in the same order;
+the only observable difference is that a transition added between two `step()` calls can be
+sampled one update later.
 """
 from typing import Optional
 
@@ -19,7 +26,7 @@ from ..replay_memory.prioritized_replay_buffer import PrioritizedReplayBuffer
 
 class FusedDqnStep:
     def __init__(self, trainer, replay_buffer, batch_size: int, process_group=None,
-                 slots: int = 2):
+                 slots: int = 2, prefetch: bool = False):
         self.trainer = trainer
         self.rb = replay_buffer
         self.B = batch_size
@@ -31,13 +38,28 @@ class FusedDqnStep:
         self.k = 0
         self.h2d_bytes = batch_size * 8
         self._side = torch.cuda.Stream(device=self.dev)
+        self._side2 = torch.cuda.Stream(device=self.dev)
         self.d2h_bytes = 4
+        self.prefetch = bool(prefetch)
         replay_buffer._flush()
         # warm-up outside capture (lazy allocations, cudaFuncSetAttribute, optimizer state)
         self._one_update(None)
         torch.cuda.synchronize()
-        for _ in range(slots):
-            self.slots.append(self._capture())
+        if self.prefetch:
+            # two fixed sets of batch tensors: update k trains on set k%2 while the sampler
+            # fills set (k+1)%2.  Set 0 gets the first real draw now; set 1 is only allocated
+            # (given indices: no random numbers consumed).
+            self._pools = [{}, {}]
+            self._batches = [None, None]
+            with self.rb.output_buffers(self._pools[0]):
+                self._batches[0] = self._sample(None)
+            with self.rb.output_buffers(self._pools[1]):
+                self._batches[1] = self.rb.sample_discrete_dqn_batch(
+                    self.B, self.A, indices=self._batches[0].indices.reshape(-1))
+            torch.cuda.synchronize()
+            slots = 2
+        for i in range(slots):
+            self.slots.append(self._capture(i))
 
     # -- one update on the current stream ---------------------------------------
     def _one_update(self, rnd_dev):
@@ -56,6 +78,29 @@ class FusedDqnStep:
             main.wait_stream(self._side)
         return self.trainer.train_batch(batch, process_group=self.pg)
 
+    def _prefetch_update(self, i, rnd_dev, overrides=None):
+        """Update on batch set i; the sampler fills set 1-i concurrently (second stream)."""
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        self._side2.wait_stream(main)
+        prepack = getattr(self.trainer, "tc_prepack", None)
+        forked = False
+        if prepack is not None:
+            with torch.cuda.stream(self._side2):
+                forked = prepack()
+        with torch.cuda.stream(self._side), self.rb.output_buffers(self._pools[1 - i]):
+            if overrides is None:
+                nxt = self._sample(rnd_dev)
+            else:
+                nxt = self.rb.sample_discrete_dqn_batch(self.B, self.A, query_dev=rnd_dev,
+                                                        overrides=overrides)
+        if forked:
+            main.wait_stream(self._side2)
+        loss = self.trainer.train_batch(self._batches[i], process_group=self.pg)
+        main.wait_stream(self._side)
+        self._batches[1 - i] = nxt
+        return loss
+
     def _sample(self, rnd_dev):
         if rnd_dev is None:
             batch = self.rb.sample_discrete_dqn_batch(self.B, self.A)
@@ -65,7 +110,7 @@ class FusedDqnStep:
             batch = self.rb.sample_discrete_dqn_batch(self.B, self.A, ranks_dev=rnd_dev)
         return batch
 
-    def _capture(self):
+    def _capture(self, i=0):
         dt = torch.float64 if self.prioritized else torch.int64
         host = torch.zeros(self.B, dtype=dt).pin_memory()
         devb = torch.zeros(self.B, dtype=dt, device=self.dev)
@@ -73,7 +118,7 @@ class FusedDqnStep:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             devb.copy_(host, non_blocking=True)
-            loss = self._one_update(devb)
+            loss = self._prefetch_update(i, devb) if self.prefetch else self._one_update(devb)
             loss_host.copy_(loss.reshape(1), non_blocking=True)
         return {"graph": g, "host": host, "dev": devb, "loss_host": loss_host,
                 "done": torch.cuda.Event(), "used": False}
@@ -97,9 +142,12 @@ class FusedDqnStep:
             q, pos, idxs = self.rb.host_queries(self.B)
             if pos:  # rare retry path: resolved on the host, run this update un-captured
                 qd = torch.from_numpy(q).to(self.dev)
-                batch = self.rb.sample_discrete_dqn_batch(self.B, self.A, query_dev=qd,
-                                                          overrides=(pos, idxs))
-                loss = self.trainer.train_batch(batch, process_group=self.pg)
+                if self.prefetch:
+                    loss = self._prefetch_update((self.k - 1) % 2, qd, overrides=(pos, idxs))
+                else:
+                    batch = self.rb.sample_discrete_dqn_batch(self.B, self.A, query_dev=qd,
+                                                              overrides=(pos, idxs))
+                    loss = self.trainer.train_batch(batch, process_group=self.pg)
                 s["loss_host"].copy_(loss.reshape(1), non_blocking=True)
                 s["done"].record()
                 s["used"] = True

@@ -249,17 +249,20 @@ def test_k2_tcgen05_matches_rows_kernel(B, S, sizes, A, acts, loss, double_q, ma
 
     r_rows, r_tc = run(False), run(True)
     assert torch.equal(r_rows["idx"], r_tc["idx"])
+    # Batch rows on which both kernels took the same activation branches.  A hidden unit whose
+    # pre-activation is within fp32 noise of 0 can get the other ReLU mask (see
+    # golden_util.grad_close), which legitimately changes that row's dZ; such rows are rare
+    # and are excluded from the element-wise dZ comparison.
+    same = torch.ones(B, dtype=torch.bool, device="cuda")
+    for i in range(len(sizes)):
+        same &= ((r_rows[f"h{i}"] > 0) == (r_tc[f"h{i}"] > 0)).all(dim=1)
+    assert float(same.float().mean()) > 0.99
     for k in r_rows:
         if k == "idx":
             continue
         x, y = r_rows[k].double(), r_tc[k].double()
         scale = max(float(x.abs().max()), 1e-30)
-        if k.startswith("dz") and x.numel() > 100000:
-            # a hidden unit whose pre-activation is within fp32 noise of 0 may get the other
-            # ReLU mask in the two kernels (see golden_util.grad_close) and the flip spreads
-            # over that row of the upstream dZ: bound the relative L2 error instead
-            # (measured 1.4e-6) -- the small shapes below stay element-wise strict
-            l2 = float((x - y).norm() / (x.norm() + 1e-30))
-            assert l2 < 1e-4, (k, l2)
-            continue
-        assert float((x - y).abs().max()) <= TOL * scale, (k, float((x - y).abs().max()), scale)
+        if k.startswith("dz"):
+            x, y = x[same], y[same]
+        # two 3xTF32 kernels, each within 1e-5 of the fp32 answer: 2e-5 between them
+        assert float((x - y).abs().max()) <= 2 * TOL * scale, (k, float((x - y).abs().max()), scale)
