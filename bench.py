@@ -267,12 +267,6 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- cpu baseline (rank 0, N == 1 only) ----
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        v, cores, sample, _ = cpu_reference_run(args.cpu_steps, 2)
-        cpu = {"value": v, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample}
-
     # ---- e2e: public API, host RNG -> pinned -> H2D, loss D2H every update ----
     fused = FusedDqnStep(trainer, rb, B, process_group=pg, prefetch=True)
     for _ in range(W):
@@ -337,6 +331,13 @@ def run_ours(args):
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     value = world * K / (dev_ms * 1e-3)
 
+    # ---- cpu baseline (rank 0, N == 1 only).  Runs LAST: its worker threads would otherwise
+    # keep spinning on the host cores while the e2e loop (host-paced) is being timed ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, sample, _ = cpu_reference_run(args.cpu_steps, 2)
+        cpu = {"value": v, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample}
+
     if rank != 0:
         return
     peaks = {}
@@ -369,7 +370,10 @@ def run_ours(args):
                                 if on_tc else
                                 "dqn_td_rows_kernel (fused TD target + loss + dZ chain, mma.sync)"),
                      "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                     "traffic": 6195200 if on_tc else None,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu "
+                                       "--set full launch (profiles/r01_ncu_dqn_td_tc.csv), bytes",
                      "peak_source": peak_src, "algorithmic_flops_per_launch": flops,
                      "kernel_ms": kern_ms,
                      "pipe_used": ("tcgen05.mma kind::tf32, 3xTF32 as 2 MMAs per k step (N=64 + N=32)"
@@ -396,7 +400,13 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        try:
+            run_ours(args)
+        finally:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized():
+                dist.destroy_process_group()
 
 
 if __name__ == "__main__":

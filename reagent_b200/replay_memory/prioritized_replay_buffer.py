@@ -89,23 +89,32 @@ class PrioritizedReplayBuffer(circular_replay_buffer.ReplayBuffer):
         (positions, indices) to override in the kernel."""
         B = len(queries)
         tree = self.sum_tree
-        total = tree._total_priority()
-        cand = set()
-        margin = 1e-9
-        for j in self._bad:
-            pj = tree.get(j)
-            if pj <= 0.0:
-                continue
-            lo = tree.prefix_mass(j) / total - margin
-            hi = (tree.prefix_mass(j) + pj) / total + margin
-            i0 = max(0, int(np.floor(lo * B)) - 1)
-            i1 = min(B - 1, int(np.ceil(hi * B)) + 1)
-            cand.update(range(i0, i1 + 1))
+        # the strata that can reach an invalid leaf depend on the tree and on the invalid set,
+        # not on this draw: cached until either changes
+        key = (B, getattr(tree, "version", 0), tree._total_priority(), tuple(sorted(self._bad)))
+        cached = getattr(self, "_cand_cache", None)
+        if cached is not None and cached[0] == key:
+            cand = cached[1]
+        else:
+            total = tree._total_priority()
+            cand = set()
+            margin = 1e-9
+            for j in self._bad:
+                pj = tree.get(j)
+                if pj <= 0.0:
+                    continue
+                lo = tree.prefix_mass(j) / total - margin
+                hi = (tree.prefix_mass(j) + pj) / total + margin
+                i0 = max(0, int(np.floor(lo * B)) - 1)
+                i1 = min(B - 1, int(np.ceil(hi * B)) + 1)
+                cand.update(range(i0, i1 + 1))
+            cand = sorted(cand)
+            self._cand_cache = (key, cand)
         pos, idxs = [], []
         allowed_attempts = self._max_sample_attempts
         walk = _lib.lib().rb200_sumtree_sample_host
         valid = self._is_index_valid
-        for i in sorted(cand):
+        for i in cand:
             index = int(walk(tree.heap.ctypes.data, tree.depth, float(queries[i])))
             if bool(valid[index]):
                 continue

@@ -108,6 +108,7 @@ class SumTree:
     # ---- batched / device plumbing -----------------------------------------
     def set_batch(self, indices: np.ndarray, values: np.ndarray) -> None:
         """Sequential SumTree.set over a batch (identical rounding to a Python loop)."""
+        self.version = getattr(self, "version", 0) + 1  # any mutation invalidates caches keyed on it
         indices = np.ascontiguousarray(indices, dtype=np.int64)
         values = np.ascontiguousarray(values, dtype=np.float64)
         if (values < 0.0).any():
