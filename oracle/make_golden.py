@@ -339,6 +339,60 @@ def preprocessor_case(name, seed=0, B=64):
 
 
 # ---------------------------------------------------------------------------
+# offline batch formatters (reagent/preprocessing/batch_preprocessor.py)
+# ---------------------------------------------------------------------------
+def batch_preprocessor_case(name, seed=0, B=48, S=6, A=4, AD=3):
+    params = ref("reagent.core.parameters")
+    pp = ref("reagent.preprocessing.preprocessor")
+    bp = ref("reagent.preprocessing.batch_preprocessor")
+    NP = params.NormalizationParameters
+    rng = np.random.RandomState(seed)
+    s_spec = {i: dict(feature_type="CONTINUOUS", mean=float(rng.randn()), stddev=float(rng.uniform(0.5, 2)))
+              for i in range(S)}
+    a_spec = {100 + i: dict(feature_type="CONTINUOUS_ACTION", min_value=-1.0 - i, max_value=2.0 + i)
+              for i in range(AD)}
+    sp = pp.Preprocessor({k: NP(**v) for k, v in s_spec.items()}, device=torch.device("cpu")).eval()
+    ap = pp.Preprocessor({k: NP(**v) for k, v in a_spec.items()}, device=torch.device("cpu")).eval()
+    mask = (rng.rand(B, A) > 0.3).astype(np.float32)
+    mask[:5] = 0.0  # terminal rows: no possible next action
+    batch = dict(
+        state_features=rng.randn(B, S).astype(np.float32) * 3,
+        state_features_presence=(rng.rand(B, S) > 0.1),
+        next_state_features=rng.randn(B, S).astype(np.float32) * 3,
+        next_state_features_presence=(rng.rand(B, S) > 0.1),
+        action=rng.randint(0, A, B).astype(np.int64),
+        next_action=rng.randint(0, A + 1, B).astype(np.int64),  # A = "not available"
+        reward=rng.randn(B).astype(np.float32), time_diff=rng.randint(1, 4, B).astype(np.float32),
+        step=rng.randint(1, 3, B).astype(np.int64), possible_actions_mask=np.ones((B, A), np.float32),
+        possible_next_actions_mask=mask, mdp_id=np.arange(B, dtype=np.int64),
+        sequence_number=rng.randint(0, 50, B).astype(np.int64),
+        action_probability=rng.uniform(0.1, 1, B).astype(np.float32))
+    tb = {k: torch.from_numpy(v) for k, v in batch.items()}
+    d = bp.DiscreteDqnBatchPreprocessor(A, sp, use_gpu=False)(tb)
+    arrays = {f"in.{k}": v for k, v in batch.items()}
+    arrays.update({"d.state": _np(d.state.float_features), "d.next_state": _np(d.next_state.float_features),
+                   "d.action": _np(d.action), "d.next_action": _np(d.next_action), "d.reward": _np(d.reward),
+                   "d.time_diff": _np(d.time_diff), "d.step": _np(d.step), "d.not_terminal": _np(d.not_terminal),
+                   "d.mdp_id": _np(d.extras.mdp_id), "d.sequence_number": _np(d.extras.sequence_number),
+                   "d.action_probability": _np(d.extras.action_probability)})
+    cb = dict(batch)
+    cb["action"] = rng.uniform(-2, 4, (B, AD)).astype(np.float32)
+    cb["next_action"] = rng.uniform(-2, 4, (B, AD)).astype(np.float32)
+    cb["action_presence"] = np.ones((B, AD), bool)
+    cb["next_action_presence"] = (rng.rand(B, AD) > 0.2)
+    cb["not_terminal"] = (rng.rand(B) > 0.2).astype(np.float32)
+    tcb = {k: torch.from_numpy(v) for k, v in cb.items()}
+    c = bp.PolicyNetworkBatchPreprocessor(sp, ap, use_gpu=False)(tcb)
+    arrays.update({f"cin.{k}": cb[k] for k in ("action", "next_action", "action_presence",
+                                              "next_action_presence", "not_terminal")})
+    arrays.update({"c.state": _np(c.state.float_features), "c.next_state": _np(c.next_state.float_features),
+                   "c.action": _np(c.action.float_features), "c.next_action": _np(c.next_action.float_features),
+                   "c.reward": _np(c.reward), "c.not_terminal": _np(c.not_terminal)})
+    _save(name, arrays, dict(kind="batch_preprocessor", s_spec={str(k): v for k, v in s_spec.items()},
+                             a_spec={str(k): v for k, v in a_spec.items()}, B=B, S=S, A=A, AD=AD))
+
+
+# ---------------------------------------------------------------------------
 # SAC / TD3: torch.randn_like is patched so that the noise draws are recorded
 # ---------------------------------------------------------------------------
 class _NoiseRecorder:
@@ -497,35 +551,38 @@ def td3_case(name, *, B=40, S=10, A=3, sizes=(16, 12), acts=("relu", "relu"), tw
     _save(name, arrays, meta)
 
 
-def main():
-    dqn_case("dqn_huber_double")
-    dqn_case("dqn_mse_single_masked", loss="mse", double_q=False, random_masks=True, seed=1)
-    dqn_case("dqn_sarsa", maxq=False, seed=2)
-    dqn_case("dqn_multistep_boost", multi_steps=3, boost={"1": 0.5, "3": -0.25}, seed=3,
-             acts=("leaky_relu", "tanh"))
-    dqn_case("dqn_timediff_odd_dims", time_diff=True, B=37, S=7, A=3, sizes=(10, 6), seed=4)
-    replay_case("replay_uniform_h1", prioritized=False, cap=100, n_add=73, B=16)
-    replay_case("replay_uniform_h3_wrap", prioritized=False, cap=64, n_add=150, B=32, horizon=3,
-                seed=1, with_extra=True)
-    replay_case("replay_uniform_h5_cont", prioritized=False, cap=128, n_add=300, B=24, horizon=5,
-                seed=2, continuous=True, gamma=0.97)
-    replay_case("replay_uniform_stack3", prioritized=False, cap=96, n_add=200, B=16, horizon=2,
-                stack=3, seed=3)
-    replay_case("replay_per_h1", prioritized=True, cap=100, n_add=90, B=32, seed=4)
-    replay_case("replay_per_h3_wrap_zero", prioritized=True, cap=64, n_add=200, B=48, horizon=3,
-                seed=5, zero_priority_every=7, p_term=0.02)
-    replay_case("replay_per_big", prioritized=True, cap=4096, n_add=6000, B=256, horizon=1,
-                seed=6, S=8, n_samples=2)
-    preprocessor_case("preprocessor_all_types")
-    sac_case("sac_twin_alpha")
-    sac_case("sac_single_fixed_alpha", twin=False, learn_alpha=False, seed=3, acts=("tanh", "leaky_relu"))
-    sac_case("sac_twin_odd_dims", B=37, S=7, A=2, sizes=(10,), acts=("relu",), seed=5, backprop=False)
-    td3_case("td3_twin")
-    td3_case("td3_single", twin=False, seed=3, acts=("tanh", "relu"), delay=3)
-    qrdqn_case("qrdqn_double")
-    qrdqn_case("qrdqn_single_masked", double_q=False, random_masks=True, seed=1, N=11)
-    qrdqn_case("qrdqn_sarsa_multistep", maxq=False, multi_steps=3, seed=2, sizes=(16,), acts=("tanh",))
+def main(only=None):
+    """Regenerate every golden case, or only the named ones (`make_golden.py name ...`)."""
+    cases = []
+    def add(fn, name, **kw):
+        cases.append((fn, name, kw))
+    add(dqn_case, "dqn_huber_double")
+    add(dqn_case, "dqn_mse_single_masked", loss="mse", double_q=False, random_masks=True, seed=1)
+    add(dqn_case, "dqn_sarsa", maxq=False, seed=2)
+    add(dqn_case, "dqn_multistep_boost", multi_steps=3, boost={"1": 0.5, "3": -0.25}, seed=3, acts=("leaky_relu", "tanh"))
+    add(dqn_case, "dqn_timediff_odd_dims", time_diff=True, B=37, S=7, A=3, sizes=(10, 6), seed=4)
+    add(replay_case, "replay_uniform_h1", prioritized=False, cap=100, n_add=73, B=16)
+    add(replay_case, "replay_uniform_h3_wrap", prioritized=False, cap=64, n_add=150, B=32, horizon=3, seed=1, with_extra=True)
+    add(replay_case, "replay_uniform_h5_cont", prioritized=False, cap=128, n_add=300, B=24, horizon=5, seed=2, continuous=True, gamma=0.97)
+    add(replay_case, "replay_uniform_stack3", prioritized=False, cap=96, n_add=200, B=16, horizon=2, stack=3, seed=3)
+    add(replay_case, "replay_per_h1", prioritized=True, cap=100, n_add=90, B=32, seed=4)
+    add(replay_case, "replay_per_h3_wrap_zero", prioritized=True, cap=64, n_add=200, B=48, horizon=3, seed=5, zero_priority_every=7, p_term=0.02)
+    add(replay_case, "replay_per_big", prioritized=True, cap=4096, n_add=6000, B=256, horizon=1, seed=6, S=8, n_samples=2)
+    add(preprocessor_case, "preprocessor_all_types")
+    add(batch_preprocessor_case, "batch_preprocessor")
+    add(sac_case, "sac_twin_alpha")
+    add(sac_case, "sac_single_fixed_alpha", twin=False, learn_alpha=False, seed=3, acts=("tanh", "leaky_relu"))
+    add(sac_case, "sac_twin_odd_dims", B=37, S=7, A=2, sizes=(10,), acts=("relu",), seed=5, backprop=False)
+    add(td3_case, "td3_twin")
+    add(td3_case, "td3_single", twin=False, seed=3, acts=("tanh", "relu"), delay=3)
+    add(qrdqn_case, "qrdqn_double")
+    add(qrdqn_case, "qrdqn_single_masked", double_q=False, random_masks=True, seed=1, N=11)
+    add(qrdqn_case, "qrdqn_sarsa_multistep", maxq=False, multi_steps=3, seed=2, sizes=(16,), acts=("tanh",))
+    for fn, name, kw in cases:
+        if only and name not in only:
+            continue
+        fn(name, **kw)
 
 
 if __name__ == "__main__":
-    main()
+    main(set(sys.argv[1:]) or None)
