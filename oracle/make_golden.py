@@ -39,6 +39,9 @@ def _save(name, arrays, meta):
 
 def _fc_params(module):
     """[(W, b)] of a reference network's FullyConnectedNetwork."""
+    if hasattr(module, "shared_network"):
+        return (_fc_params(module.shared_network) + _fc_params(module.advantage_network)
+                + _fc_params(module.value_network))
     out = []
     for seq in module.fc.dnn:
         lin = seq[0]
@@ -47,6 +50,10 @@ def _fc_params(module):
 
 
 def _dump_net(arrays, prefix, module):
+    if hasattr(module, "shared_network"):  # DuelingQNetwork: three FullyConnectedDQN parts
+        for part in ("shared", "advantage", "value"):
+            _dump_net(arrays, f"{prefix}.{part}", getattr(module, part + "_network"))
+        return
     for i, (w, b) in enumerate(_fc_params(module)):
         arrays[f"{prefix}.W{i}"] = _np(w).copy()
         arrays[f"{prefix}.b{i}"] = _np(b).copy()
@@ -55,14 +62,18 @@ def _dump_net(arrays, prefix, module):
 # ---------------------------------------------------------------------------
 def dqn_case(name, *, B=48, S=12, A=5, sizes=(24, 20), acts=("relu", "relu"), loss="huber",
              double_q=True, maxq=True, multi_steps=None, time_diff=False, boost=None,
-             random_masks=False, gamma=0.97, tau=0.05, lr=1e-2, seed=0):
+             random_masks=False, gamma=0.97, tau=0.05, lr=1e-2, seed=0, dueling=False):
     rlt = ref("reagent.core.types")
     params = ref("reagent.core.parameters")
     dqn_mod = ref("reagent.models.dqn")
     tr = ref("reagent.training.dqn_trainer")
     union = ref("reagent.optimizer.union")
     torch.manual_seed(seed)
-    q = dqn_mod.FullyConnectedDQN(S, A, list(sizes), list(acts))
+    if dueling:
+        duel = ref("reagent.models.dueling_q_network")
+        q = duel.DuelingQNetwork.make_fully_connected(S, A, list(sizes), list(acts))
+    else:
+        q = dqn_mod.FullyConnectedDQN(S, A, list(sizes), list(acts))
     # biases are 0 at init in the reference; perturb so that bias paths are exercised
     with torch.no_grad():
         for _, b in _fc_params(q):
@@ -121,7 +132,7 @@ def dqn_case(name, *, B=48, S=12, A=5, sizes=(24, 20), acts=("relu", "relu"), lo
     _dump_net(arrays, "qtN", qt)
     meta = dict(kind="dqn", B=B, S=S, A=A, sizes=list(sizes), acts=list(acts), loss=loss,
                 double_q=double_q, maxq=maxq, multi_steps=multi_steps, time_diff=time_diff,
-                boost=boost, gamma=gamma, tau=tau, lr=lr, n_updates=N_UPDATES)
+                boost=boost, gamma=gamma, tau=tau, lr=lr, n_updates=N_UPDATES, dueling=dueling)
     _save(name, arrays, meta)
 
 
@@ -561,6 +572,9 @@ def main(only=None):
     add(dqn_case, "dqn_sarsa", maxq=False, seed=2)
     add(dqn_case, "dqn_multistep_boost", multi_steps=3, boost={"1": 0.5, "3": -0.25}, seed=3, acts=("leaky_relu", "tanh"))
     add(dqn_case, "dqn_timediff_odd_dims", time_diff=True, B=37, S=7, A=3, sizes=(10, 6), seed=4)
+    add(dqn_case, "dqn_dueling_double", dueling=True, sizes=(24, 16), seed=6)
+    add(dqn_case, "dqn_dueling_mse_masked", dueling=True, sizes=(16,), acts=("tanh",), loss="mse",
+        double_q=False, random_masks=True, B=37, S=7, A=3, seed=7)
     add(replay_case, "replay_uniform_h1", prioritized=False, cap=100, n_add=73, B=16)
     add(replay_case, "replay_uniform_h3_wrap", prioritized=False, cap=64, n_add=150, B=32, horizon=3, seed=1, with_extra=True)
     add(replay_case, "replay_uniform_h5_cont", prioritized=False, cap=128, n_add=300, B=24, horizon=5, seed=2, continuous=True, gamma=0.97)

@@ -43,6 +43,9 @@ def make_net(dims: List[int], acts: List[str], gen: torch.Generator) -> Net:
 
 
 def clone_net(net: Net, requires_grad: bool = False) -> Net:
+    if net.get("kind") == "dueling":
+        return {"kind": "dueling", **{k: clone_net(net[k], requires_grad)
+                                      for k in ("shared", "adv", "val")}}
     return {
         "W": [w.detach().clone().requires_grad_(requires_grad) for w in net["W"]],
         "b": [x.detach().clone().requires_grad_(requires_grad) for x in net["b"]],
@@ -51,6 +54,8 @@ def clone_net(net: Net, requires_grad: bool = False) -> Net:
 
 
 def net_params(net: Net) -> List[torch.Tensor]:
+    if net.get("kind") == "dueling":  # registration order of DuelingQNetwork's sub-modules
+        return net_params(net["shared"]) + net_params(net["adv"]) + net_params(net["val"])
     out = []
     for w, b in zip(net["W"], net["b"]):
         out += [w, b]
@@ -58,7 +63,14 @@ def net_params(net: Net) -> List[torch.Tensor]:
 
 
 def mlp(net: Net, x: torch.Tensor) -> torch.Tensor:
-    """FullyConnectedNetwork.forward (fully_connected_network.py:157-163)."""
+    """FullyConnectedNetwork.forward (fully_connected_network.py:157-163); for a dueling net
+    DuelingQNetwork._get_values (reagent/models/dueling_q_network.py:92-103):
+    q = value + (advantage - mean over the non-batch dims of advantage)."""
+    if net.get("kind") == "dueling":
+        shared = mlp(net["shared"], x)
+        value = mlp(net["val"], shared)
+        raw_adv = mlp(net["adv"], shared)
+        return value + (raw_adv - raw_adv.mean(dim=1, keepdim=True))
     for w, b, a in zip(net["W"], net["b"], net["act"]):
         x = _ACT[a](F.linear(x, w, b))
     return x

@@ -42,6 +42,13 @@ class ParamArena:
         self.grad_ready = False
         self._desc = None
 
+    # -- hooks for arenas with derived regions (models/dueling_q_network.py) ------
+    def refresh(self):
+        """Bring derived parameters up to date before the kernels read the arena (no-op here)."""
+
+    def finish_grads(self):
+        """Map gradients of derived parameters back onto the true ones (no-op here)."""
+
     # -- views ---------------------------------------------------------------
     def weight_view(self, flat, l):
         o, i = self.dims[l + 1], self.dims[l]

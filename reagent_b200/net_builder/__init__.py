@@ -5,8 +5,8 @@ from dataclasses import dataclass, field
 from typing import List
 
 from ..core.parameters import NormalizationData
-from ..models import (FullyConnectedActor, FullyConnectedCritic, FullyConnectedDQN,
-                      GaussianFullyConnectedActor)
+from ..models import (DuelingQNetwork, FullyConnectedActor, FullyConnectedCritic,
+                      FullyConnectedDQN, GaussianFullyConnectedActor)
 from ..preprocessing.normalization import get_num_output_features
 
 
@@ -28,6 +28,23 @@ class FullyConnected:
                                  sizes=self.sizes, activations=self.activations,
                                  dropout_ratio=self.dropout_ratio,
                                  use_batch_norm=self.use_batch_norm)
+
+
+@dataclass
+class Dueling:
+    """reagent/net_builder/discrete_dqn/dueling.py:16-40 (the default of the DiscreteDQN manager)"""
+    sizes: List[int] = field(default_factory=lambda: [256, 128])
+    activations: List[str] = field(default_factory=lambda: ["relu", "relu"])
+
+    def __post_init__(self):
+        assert len(self.sizes) == len(self.activations), (
+            f"Must have the same numbers of sizes and activations; got: "
+            f"{self.sizes}, {self.activations}")
+
+    def build_q_network(self, state_feature_config, state_normalization_data: NormalizationData,
+                        output_dim: int):
+        return DuelingQNetwork.make_fully_connected(_dim(state_normalization_data), output_dim,
+                                                    self.sizes, self.activations)
 
 
 @dataclass

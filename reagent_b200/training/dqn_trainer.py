@@ -131,6 +131,8 @@ class DQNTrainer(DQNTrainerBaseLightning):
         training `_td_step` (which then skips the packing).  The images depend only on the
         parameters, so a caller may run this on a side stream next to the replay sampling
         (fused_step.py).  Returns False when K2 runs on the row-tile kernel instead."""
+        self.q_network.arena.refresh()          # derived parameters (dueling head) first
+        self.q_network_target.arena.refresh()
         qd, qtd = self.q_network.arena.desc(), self.q_network_target.arena.desc()
         key = (int(bool(self.double_q_learning)), 1)
         pack = self._tc_pack_for(key, qd, self.q_network.arena.flat.device)
@@ -189,6 +191,8 @@ class DQNTrainer(DQNTrainerBaseLightning):
         a.loss_partials = ws["loss_partials"].data_ptr()
         a.loss = ws["loss"].data_ptr()
         a.tile_counter = ws["counter"].data_ptr()
+        self.q_network.arena.refresh()          # no-op for plain MLPs; folds a dueling head
+        self.q_network_target.arena.refresh()
         qd, qtd = self.q_network.arena.desc(), self.q_network_target.arena.desc()
         ev = self._kernel_events
         if ev is not None:
@@ -212,6 +216,7 @@ class DQNTrainer(DQNTrainerBaseLightning):
             ev.append((e0, e1))
         if do_backward:
             wgrad(self.q_network.arena, ws["net"], state, B)
+            self.q_network.arena.finish_grads()  # dueling: folded-layer gradient -> true parameters
         self.all_action_scores = ws["scores"]
         return ws["loss"].reshape(())
 

@@ -16,6 +16,14 @@ def load(name):
 
 
 def oracle_net(arrays, prefix, acts, requires_grad=False):
+    if f"{prefix}.shared.W0" in arrays:
+        # DuelingQNetwork.make_fully_connected (dueling_q_network.py:48-90): the shared trunk ends
+        # in a linear layer; both heads are [E -> E/2 (last activation) -> out (linear)]
+        head = [acts[-2], "linear"]
+        return {"kind": "dueling",
+                "shared": oracle_net(arrays, prefix + ".shared", list(acts[:-2]) + ["linear"], requires_grad),
+                "adv": oracle_net(arrays, prefix + ".advantage", head, requires_grad),
+                "val": oracle_net(arrays, prefix + ".value", head, requires_grad)}
     W, b = [], []
     i = 0
     while f"{prefix}.W{i}" in arrays:
@@ -25,8 +33,23 @@ def oracle_net(arrays, prefix, acts, requires_grad=False):
     return {"W": W, "b": b, "act": list(acts)}
 
 
+def net_pairs(arrays, prefix):
+    """[(W, b)] arrays of a dumped network in parameter order (dueling: shared, advantage, value)."""
+    if f"{prefix}.shared.W0" in arrays:
+        return sum((net_pairs(arrays, f"{prefix}.{part}") for part in ("shared", "advantage", "value")), [])
+    out, i = [], 0
+    while f"{prefix}.W{i}" in arrays:
+        out.append((arrays[f"{prefix}.W{i}"], arrays[f"{prefix}.b{i}"]))
+        i += 1
+    return out
+
+
 def load_into_module(arrays, prefix, module):
     """Copy golden weights into a reagent_b200 model (module.fc.dnn[i][0] Linear views)."""
+    if hasattr(module, "shared_network"):
+        for part in ("shared", "advantage", "value"):
+            load_into_module(arrays, f"{prefix}.{part}", getattr(module, part + "_network"))
+        return
     fc = module.fc if hasattr(module, "fc") else module
     with torch.no_grad():
         for i, seq in enumerate(fc.dnn):

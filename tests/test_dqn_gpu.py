@@ -28,11 +28,14 @@ def _assert_k2(t, path):
 
 def _build_trainer(meta, arrays=None, dev="cuda"):
     from reagent_b200.core.parameters import EvaluationParameters, RLParameters
-    from reagent_b200.models import FullyConnectedDQN
+    from reagent_b200.models import DuelingQNetwork, FullyConnectedDQN
     from reagent_b200.optimizer import Optimizer__Union
     from reagent_b200.training import DQNTrainer
 
-    q = FullyConnectedDQN(meta["S"], meta["A"], meta["sizes"], meta["acts"])
+    if meta.get("dueling"):
+        q = DuelingQNetwork.make_fully_connected(meta["S"], meta["A"], meta["sizes"], meta["acts"])
+    else:
+        q = FullyConnectedDQN(meta["S"], meta["A"], meta["sizes"], meta["acts"])
     qt = q.get_target_network()
     if arrays is not None:
         G.load_into_module(arrays, "q0", q)
@@ -67,13 +70,13 @@ def _check_against_golden(t, arrays, meta, losses):
     for it, l in enumerate(losses):
         ref = arrays["losses"][it]
         assert abs(l - ref) <= TOL * max(1.0, abs(ref)), (it, l, ref)
-    q, qt = t.q_network, t.q_network_target
-    for i, seq in enumerate(q.fc.dnn):
-        assert G.rel_err(seq[0].weight, arrays[f"qN.W{i}"]) < TOL
-        assert G.rel_err(seq[0].bias, arrays[f"qN.b{i}"]) < TOL
-    for i, seq in enumerate(qt.fc.dnn):
-        assert G.rel_err(seq[0].weight, arrays[f"qtN.W{i}"]) < TOL
-        assert G.rel_err(seq[0].bias, arrays[f"qtN.b{i}"]) < TOL
+    for net, prefix in ((t.q_network, "qN"), (t.q_network_target, "qtN")):
+        ps = list(net.parameters())
+        pairs = G.net_pairs(arrays, prefix)
+        assert len(ps) == 2 * len(pairs)
+        for i, (w, b) in enumerate(pairs):
+            assert G.rel_err(ps[2 * i], w) < TOL, (prefix, i)
+            assert G.rel_err(ps[2 * i + 1], b) < TOL, (prefix, i)
 
 
 @pytest.mark.parametrize("path", K2_PATHS)
@@ -266,3 +269,35 @@ def test_k2_tcgen05_matches_rows_kernel(B, S, sizes, A, acts, loss, double_q, ma
             x, y = x[same], y[same]
         # two 3xTF32 kernels, each within 1e-5 of the fp32 answer: 2e-5 between them
         assert float((x - y).abs().max()) <= 2 * TOL * scale, (k, float((x - y).abs().max()), scale)
+
+
+def test_dueling_forward_heads_and_state_dict():
+    """DuelingQNetwork: the folded single-launch forward, the head-by-head evaluation on the
+    true parameters and the reference's q(s) agree; state_dict keys are the reference's."""
+    from reagent_b200.core import types as rlt
+    from reagent_b200.models import DuelingQNetwork
+
+    arrays, meta = G.load("dqn_dueling_double")
+    q = DuelingQNetwork.make_fully_connected(meta["S"], meta["A"], meta["sizes"], meta["acts"])
+    assert list(q.state_dict().keys())[:2] == ["shared_network.fc.dnn.0.0.weight",
+                                               "shared_network.fc.dnn.0.0.bias"]
+    assert "advantage_network.fc.dnn.1.0.weight" in q.state_dict()
+    assert tuple(q.state_dict()["value_network.fc.dnn.1.0.weight"].shape) == (1, meta["sizes"][-1] // 2)
+    G.load_into_module(arrays, "q0", q)
+    q = q.cuda()
+    x = rlt.FeatureData(torch.from_numpy(arrays["batch.state"]).cuda())
+    out = q(x)
+    assert G.rel_err(out, arrays["all_q0"]) < TOL
+    value, raw_adv, adv, qv = q._get_values(x)
+    assert value.shape == (meta["B"], 1) and raw_adv.shape == (meta["B"], meta["A"])
+    assert G.rel_err(qv, arrays["all_q0"]) < TOL
+    assert float(adv.mean(dim=1).abs().max()) < 1e-6
+    mask = torch.ones(meta["B"], meta["A"], device="cuda")
+    mask[:, 0] = 0
+    assert float(q(x, mask)[:, 0].max()) < -1e9
+    # a copy through state_dict (what loading a reference checkpoint does) reproduces q
+    q2 = DuelingQNetwork.make_fully_connected(meta["S"], meta["A"], meta["sizes"], meta["acts"]).cuda()
+    q2.load_state_dict(q.state_dict())
+    assert torch.equal(q2(x), out)
+    qt = q.get_target_network()
+    assert torch.equal(qt(x), out)

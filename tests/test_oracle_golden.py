@@ -7,7 +7,7 @@ from oracle import td_oracle as O
 from tests import golden_util as G
 
 DQN_CASES = ["dqn_huber_double", "dqn_mse_single_masked", "dqn_sarsa", "dqn_multistep_boost",
-             "dqn_timediff_odd_dims"]
+             "dqn_timediff_odd_dims", "dqn_dueling_double", "dqn_dueling_mse_masked"]
 
 
 def _dqn_kwargs(meta, batch):
@@ -40,11 +40,11 @@ def test_dqn_oracle_matches_reference(name):
             for i, g in enumerate(grads):
                 assert G.rel_err(g, arrays[f"grad0.{i}"]) < 1e-6
             assert G.rel_err(aux["all_q"], arrays["all_q0"]) < 1e-6
-    for i in range(len(q["W"])):
-        assert G.rel_err(q["W"][i], arrays[f"qN.W{i}"]) < 1e-6
-        assert G.rel_err(q["b"][i], arrays[f"qN.b{i}"]) < 1e-6
-        assert G.rel_err(qt["W"][i], arrays[f"qtN.W{i}"]) < 1e-6
-        assert G.rel_err(qt["b"][i], arrays[f"qtN.b{i}"]) < 1e-6
+    for net, prefix in ((q, "qN"), (qt, "qtN")):
+        ps = O.net_params(net)
+        for i, (w, b) in enumerate(G.net_pairs(arrays, prefix)):
+            assert G.rel_err(ps[2 * i], w) < 1e-6
+            assert G.rel_err(ps[2 * i + 1], b) < 1e-6
 
 
 # ---------------------------------------------------------------------------
