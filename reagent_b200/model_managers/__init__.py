@@ -5,11 +5,11 @@ actor_critic/td3.py:70-102): build the networks from the net builders, copy the 
 everything to the trainer.  Policies, serving modules, data modules and reporters are out of
 scope."""
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional
+from typing import Union, Dict, List, Optional
 
 from ..core.parameters import (EvaluationParameters, NormalizationData, NormalizationKey,
                                RLParameters)
-from ..net_builder import (ActorFullyConnected, FullyConnected, GaussianFullyConnected,
+from ..net_builder import (ActorFullyConnected, Dueling, FullyConnected, GaussianFullyConnected,
                            ParametricFullyConnected, Quantile)
 from ..optimizer import Optimizer__Union
 from ..training import DQNTrainer, QRDQNTrainer, SACTrainer, TD3Trainer
@@ -28,7 +28,8 @@ class DiscreteDQN:
     double_q_learning: bool = True
     minibatch_size: int = 1024
     optimizer: Optimizer__Union = field(default_factory=Optimizer__Union.default)
-    net_builder: FullyConnected = field(default_factory=FullyConnected)
+    # reagent/model_managers/discrete/discrete_dqn.py:33-36: the reference defaults to Dueling
+    net_builder: Union[Dueling, FullyConnected] = field(default_factory=Dueling)
     eval_parameters: EvaluationParameters = field(
         default_factory=lambda: EvaluationParameters(calc_cpe_in_training=False))
 
