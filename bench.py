@@ -5,9 +5,9 @@
   state_dim=128, actions=16, batch=4096, prioritized replay (sum tree, capacity 2^20).
 
 One "step" = one full update INCLUDING drawing the minibatch: replay sample kernel (tree
-walk + gather + batch formatting) -> weight-image pack (hi/lo TF32 planes for the tensor
-cores) -> fused TD-target/loss/backward kernel -> weight-gradient kernel -> fused Adam +
-soft-target-update kernel.
+walk + gather + batch formatting) -> fused TD-target/loss/backward kernel (tcgen05) ->
+weight-gradient kernel -> fused Adam + soft-target-update kernel (which also writes the hi/lo
+TF32 weight images the next TD step feeds to the tensor cores).
 
   value : K updates captured in ONE CUDA graph with all random numbers already in HBM
           (device-timed, CUDA events, max over ranks).
@@ -364,7 +364,7 @@ def run_ours(args):
                 "api": "reagent_b200.training.fused_step.FusedDqnStep(prefetch=True).step(): every "
                        "step draws one minibatch (host RNG -> pinned -> H2D -> sample kernel) and "
                        "trains on one; the sampler runs one update ahead on a second stream"},
-        "gpu_launches": (5 if on_tc else 4) * K,
+        "gpu_launches": 4 * K,  # sample, TD step, weight gradients, Adam(+Polyak+weight images)
         "clocks": clk,
         "roofline": {"kernel": ("dqn_td_tc_kernel (fused TD target + loss + dZ chain on tcgen05/TMEM)"
                                 if on_tc else

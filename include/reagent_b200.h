@@ -320,6 +320,14 @@ typedef struct rb200_adam_args {
   float one_minus_tau;    /* float(1.0 - tau) computed in double on the host */
   float* exp_out;         /* [n] or NULL: exp(new param) (SAC: entropy_temperature =
                              log_alpha.exp(), sac_trainer.py:322) */
+  /* Optional: also write the hi/lo tensor-core weight images of the UPDATED parameters (and of
+   * the updated target) for the next rb200_dqn_td_step_tc, which can then be called with
+   * weights_packed = 1 -- the work of rb200_dqn_tc_pack without its launch.  tc_net describes
+   * the network whose arena `params` is (tc_net->params == params); needs `target`. */
+  const rb200_mlp_t* tc_net;   /* NULL: no packing */
+  void* tc_pack_ws;            /* the scratch buffer of rb200_dqn_td_step_tc */
+  int64_t tc_pack_ws_bytes;
+  int32_t tc_do_backward;      /* also the transposed images of the backward */
 } rb200_adam_args_t;
 int rb200_adam_soft_update(const rb200_adam_args_t* a, void* stream);
 /* stand-alone Polyak update (SoftUpdate.step when not fused) */

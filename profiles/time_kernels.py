@@ -32,9 +32,11 @@ def timeit(fn, n=50):
 opt = t.optimizers()[0]
 from reagent_b200 import _lib
 t._td_step(batches[0])
-qd, qtd, a, wsc, keep = t._last_td_call
+qd, qtd, a, wsc, keep, pack = t._last_td_call
 st = _lib.cur_stream()
-print("K2 dqn_td_rows kernel (device) us", timeit(lambda i: _lib.lib().rb200_dqn_td_step(qd, qtd, a, wsc, st), 200))
+print("K2 dqn_td_rows kernel (mma.sync) us", timeit(lambda i: _lib.lib().rb200_dqn_td_step(qd, qtd, a, wsc, st), 200))
+if pack is not None:
+    print("K2 dqn_td_tc kernel (tcgen05, pack+kernel) us", timeit(lambda i: _lib.lib().rb200_dqn_td_step_tc(qd, qtd, a, wsc, pack.data_ptr(), pack.numel(), 0, st), 200))
 a.do_backward = 0
 print("K2 fwd+loss only (device) us", timeit(lambda i: _lib.lib().rb200_dqn_td_step(qd, qtd, a, wsc, st), 200))
 a.do_backward = 1

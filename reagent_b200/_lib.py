@@ -85,6 +85,10 @@ class AdamArgsT(C.Structure):
         ("tau", C.c_float),
         ("one_minus_tau", C.c_float),
         ("exp_out", _vp),
+        ("tc_net", C.POINTER(MlpT)),
+        ("tc_pack_ws", _vp),
+        ("tc_pack_ws_bytes", C.c_int64),
+        ("tc_do_backward", C.c_int32),
     ]
 
 

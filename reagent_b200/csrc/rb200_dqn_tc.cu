@@ -33,14 +33,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "rb200_dqn_tc_layout.cuh"
 #include "rb200_umma.cuh"
 
 namespace rb200 {
 
 constexpr int kQR = 32;                                   // batch rows per CTA
-constexpr int kQKC = 32;                                  // contraction elements per weight chunk
 constexpr int kQStages = 3;                               // ring depth
-constexpr int kQFullLbo = 128 * 16 + 16;                  // A quad stride of a full 128-row tile
 constexpr int kQStageBytes = 2 * (kQKC / 4) * kQFullLbo;  // hi + lo planes of one chunk
 // B operand (activations): per k quad 64 rows of 16 B -- rows 0-31 hold the hi parts of the 32
 // batch rows, rows 32-63 their lo parts -- plus 16 B of padding.  One N = 64 MMA against W_hi
@@ -79,37 +78,6 @@ struct QDev {
   long long* dbg;  // optional timeline of block 0: [step][8] clock64 stamps (profiling builds)
   QStep steps[kQMaxSteps];
 };
-
-__host__ __device__ __forceinline__ int round_up8(int x) { return (x + 7) & ~7; }
-
-struct ChunkGeo {
-  uint32_t off, bytes, lbo;
-  int ksteps, k0q;
-};
-// geometry of chunk (feature tile t, k chunk c) inside the image of an [N x K] operand
-__host__ __device__ __forceinline__ ChunkGeo chunk_geo(int N, int K, int t, int c) {
-  ChunkGeo g;
-  const int rows = N - 128 * t;
-  const int rows8 = round_up8(rows < 128 ? rows : 128);
-  g.lbo = (uint32_t)(rows8 * 16 + 16);
-  const int kl = K - kQKC * c;
-  const int kl8 = round_up8(kl < kQKC ? kl : kQKC);
-  g.bytes = 2u * (uint32_t)(kl8 / 4) * g.lbo;
-  g.off = (uint32_t)t * (2u * (uint32_t)(round_up8(K) / 4) * kQFullLbo) +
-          (uint32_t)c * (2u * (kQKC / 4) * g.lbo);
-  g.ksteps = kl8 / 8;
-  g.k0q = c * (kQKC / 4);
-  return g;
-}
-static uint32_t image_bytes(int N, int K) {
-  uint32_t tot = 0;
-  for (int t = 0; t < ceil_div(N, 128); ++t) {
-    const int rows = N - 128 * t;
-    const int rows8 = round_up8(rows < 128 ? rows : 128);
-    tot += 2u * (uint32_t)(round_up8(K) / 4) * (uint32_t)(rows8 * 16 + 16);
-  }
-  return tot;
-}
 
 // ---------------------------------------------------------------------------
 // weight packing: fp32 arena -> hi/lo UMMA images
@@ -167,7 +135,7 @@ __global__ void __launch_bounds__(256) dqn_tc_pack_kernel(const PackDev p) {
     for (int u = 0; u < U; ++u) {
       if (o[u] < 0) continue;
       float h, l;
-      split1(v[u], h, l);
+      tf32_split(v[u], h, l);
       hi[o[u]] = h;
       lo[o[u]] = l;
     }
@@ -705,7 +673,15 @@ static QPlan make_plan(const rb200_mlp_t* qn, const rb200_mlp_t* qtn, int double
   if (do_backward) for (int l = 1; l < L; ++l) off_bw[l] = add_job(qn, l, 1);
   pl.pack.njobs = nj;
   pl.pack_chunks = nchunks;
-  pl.pack_bytes = (int64_t)off + 4096;  // slack: partial tiles are over-read by design (in smem only)
+  {
+    // the Adam kernel writes the same images from rb200_dqn_tc_layout.cuh's table
+    const TcImages im = tc_images(qn, do_backward);
+    pl.pack_bytes = im.total_bytes;
+    bool same = im.total_bytes == (int64_t)off + 4096;
+    for (int l = 0; l < L; ++l) same = same && im.on_fwd[l] == off_on[l] && im.tg_fwd[l] == off_tg[l];
+    if (do_backward) for (int l = 1; l < L; ++l) same = same && im.on_bwd[l] == off_bw[l];
+    if (!same) return pl;  // ok stays false: layout tables disagree (a bug, not a user error)
+  }
 
   // steps
   int ns = 0;

@@ -1,7 +1,9 @@
 // reagent_b200 -- weight-gradient, gradient-reduce, fused Adam + soft-update kernels (K3).
 #include <math.h>
 
-#include "rb200_common.cuh"
+#include <stdlib.h>
+
+#include "rb200_dqn_tc_layout.cuh"
 
 namespace rb200 {
 
@@ -198,7 +200,40 @@ __global__ void grad_reduce_kernel(const float* __restrict__ gpart, int splits, 
 // ---------------------------------------------------------------------------
 struct AdamDev {
   rb200_adam_args_t a;
+  TcPackView pv;
 };
+
+// hi/lo images of one updated weight (and of its updated target) for the tcgen05 TD kernel
+__device__ __forceinline__ void adam_pack_weight(const TcPackView& pv, long long i, float p,
+                                                 bool has_target, float tgt) {
+  for (int l = 0; l < pv.n_layers; ++l) {
+    const int N = pv.dims[l + 1], K = pv.dims[l];
+    const long long rel = i - pv.w_off[l];
+    if (rel < 0 || rel >= (long long)N * K) continue;
+    const int m = (int)(rel / K), k = (int)(rel - (long long)m * K);
+    uint32_t hi, lo;
+    float h, lw;
+    image_elem(N, K, m, k, hi, lo);
+    tf32_split(p, h, lw);
+    float* f = pv.pack + pv.on_fwd[l] / 4;
+    f[hi] = h;
+    f[lo] = lw;
+    if (has_target) {
+      float th, tl;
+      tf32_split(tgt, th, tl);
+      float* ft = pv.pack + pv.tg_fwd[l] / 4;
+      ft[hi] = th;
+      ft[lo] = tl;
+    }
+    if (pv.has_bwd && l >= 1) {  // transposed operand: rows = K_l features, contraction = N_l
+      image_elem(K, N, k, m, hi, lo);
+      float* fb = pv.pack + pv.on_bwd[l] / 4;
+      fb[hi] = h;
+      fb[lo] = lw;
+    }
+    return;
+  }
+}
 
 __global__ void __launch_bounds__(256) adam_soft_kernel(const AdamDev d) {
   const rb200_adam_args_t& a = d.a;
@@ -251,10 +286,13 @@ __global__ void __launch_bounds__(256) adam_soft_kernel(const AdamDev d) {
     a.exp_avg[i] = m;
     a.exp_avg_sq[i] = v;
     if (a.exp_out) a.exp_out[i] = expf(p);
+    float tn = 0.f;
     if (a.target) {
       const float tg = a.target[i];
-      a.target[i] = __fadd_rn(__fmul_rn(a.tau, p), __fmul_rn(a.one_minus_tau, tg));
+      tn = __fadd_rn(__fmul_rn(a.tau, p), __fmul_rn(a.one_minus_tau, tg));
+      a.target[i] = tn;
     }
+    if (d.pv.pack) adam_pack_weight(d.pv, i, p, a.target != nullptr, tn);
   }
   // last block to finish bumps the step counter (every block has read it by then)
   __syncthreads();
@@ -282,9 +320,12 @@ using namespace rb200;
 extern "C" int rb200_wgrad_splits(int batch) {
   // enough batch splits that even a single 64x64 tile layer fills a good part of the
   // 148 SMs; rows per split stay a multiple of the 32-row staging step.
-  int s = batch / 256;
+  const char* e = getenv("RB200_WGRAD_ROWS");  // tuning knob (rows per split), default 256
+  int rows = e ? atoi(e) : 256;
+  if (rows < 32) rows = 32;
+  int s = batch / rows;
   if (s < 1) s = 1;
-  if (s > 32) s = 32;
+  if (s > 64) s = 64;
   return s;
 }
 
@@ -338,6 +379,25 @@ extern "C" int rb200_adam_soft_update(const rb200_adam_args_t* a, void* stream) 
   if (a->n <= 0 || a->splits <= 0) { set_last_error("rb200_adam_soft_update: bad n/splits"); return RB200_E_INVALID; }
   AdamDev d;
   d.a = *a;
+  d.a.tc_net = nullptr;  // host pointer: not for the device
+  d.pv.pack = nullptr;
+  if (a->tc_net && a->tc_pack_ws) {
+    const rb200_mlp_t* q = a->tc_net;
+    if (int rc = validate_mlp(q, "tc_net")) return rc;
+    if (q->params != a->params || !a->target) { set_last_error("rb200_adam_soft_update: tc packing needs tc_net->params == params and a target"); return RB200_E_INVALID; }
+    const TcImages im = tc_images(q, a->tc_do_backward);
+    if (a->tc_pack_ws_bytes < im.total_bytes) { set_last_error("rb200_adam_soft_update: pack workspace too small"); return RB200_E_INVALID; }
+    d.pv.n_layers = q->n_layers;
+    for (int l = 0; l <= kMaxLayers; ++l) d.pv.dims[l] = im.dims[l];
+    for (int l = 0; l < kMaxLayers; ++l) {
+      d.pv.w_off[l] = l < q->n_layers ? q->w_off[l] : 0;
+      d.pv.on_fwd[l] = im.on_fwd[l];
+      d.pv.tg_fwd[l] = im.tg_fwd[l];
+      d.pv.on_bwd[l] = im.on_bwd[l];
+    }
+    d.pv.has_bwd = im.has_bwd;
+    d.pv.pack = static_cast<float*>(a->tc_pack_ws);
+  }
   int blocks = (int)((a->n + 255) / 256);
   if (blocks > 148 * 4) blocks = 148 * 4;
   adam_soft_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d);

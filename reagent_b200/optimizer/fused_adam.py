@@ -68,8 +68,10 @@ class FusedAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def fused_step(self, target: Optional[ParamArena] = None, tau: float = 0.0,
                    grad: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
-                   exp_out: Optional[torch.Tensor] = None):
-        """Adam step (+ Polyak update of `target` with the NEW parameters when given)."""
+                   exp_out: Optional[torch.Tensor] = None, tc_pack=None):
+        """Adam step (+ Polyak update of `target` with the NEW parameters when given).
+        `tc_pack = (pack_tensor, do_backward)`: also write the tensor-core weight images of the
+        updated network and target for the next rb200_dqn_td_step_tc (needs `target`)."""
         self._ensure_state()
         a = self.arena
         if grad is None:
@@ -105,9 +107,23 @@ class FusedAdam(torch.optim.Optimizer):
             args.tau = 0.0
             args.one_minus_tau = 1.0
         args.exp_out = None if exp_out is None else exp_out.data_ptr()
+        desc = None
+        if tc_pack is not None and target is not None:
+            import ctypes as C
+
+            desc = a.desc()  # kept alive until the launch returns
+            args.tc_net = C.pointer(desc)
+            args.tc_pack_ws = tc_pack[0].data_ptr()
+            args.tc_pack_ws_bytes = tc_pack[0].numel()
+            args.tc_do_backward = int(tc_pack[1])
         _lib.check(_lib.lib().rb200_adam_soft_update(args, _lib.cur_stream()),
                    "rb200_adam_soft_update")
         a.grad_ready = False
+        # every library write to an arena bumps its epoch (caches keyed on parameter contents)
+        a.data_epoch = getattr(a, "data_epoch", 0) + 1
+        if target is not None:
+            target.data_epoch = getattr(target, "data_epoch", 0) + 1
+        return desc is not None
 
     @torch.no_grad()
     def step(self, closure=None):

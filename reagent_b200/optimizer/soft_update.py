@@ -56,6 +56,7 @@ class SoftUpdate(torch.optim.Optimizer):
                 _lib.lib().rb200_soft_update(ta.flat.data_ptr(), sa.flat.data_ptr(), ta.n,
                                              float(tau), float(1.0 - tau), _lib.cur_stream()),
                 "rb200_soft_update")
+            ta.data_epoch = getattr(ta, "data_epoch", 0) + 1
         return loss
 
     def zero_grad(self, set_to_none: bool = True):

@@ -126,6 +126,27 @@ class DQNTrainer(DQNTrainerBaseLightning):
             cache[key] = pack
         return pack
 
+    def _tc_state(self):
+        """What the tensor-core weight images were built from: identity, torch version counter
+        (in-place torch ops, e.g. load_state_dict) and library write epoch of both arenas."""
+        qa, ta = self.q_network.arena, self.q_network_target.arena
+        return (id(qa.flat), qa.flat._version, getattr(qa, "data_epoch", 0),
+                id(ta.flat), ta.flat._version, getattr(ta, "data_epoch", 0))
+
+    def _tc_images_current(self) -> bool:
+        return self.__dict__.get("_tc_images_state") == self._tc_state()
+
+    def _tc_pack_in_adam(self):
+        """(pack, do_backward) for FusedAdam.fused_step when the Adam kernel can write the
+        images itself: plain MLP arenas only (a dueling head is re-folded after the step)."""
+        from ..models.arena import ParamArena
+
+        qa = self.q_network.arena
+        if type(qa) is not ParamArena or os.environ.get("RB200_NO_ADAM_PACK"):
+            return None
+        pack = self._tc_pack_for((int(bool(self.double_q_learning)), 1), qa.desc(), qa.flat.device)
+        return None if pack is None else (pack, 1)
+
     def tc_prepack(self) -> bool:
         """Build the weight images of the tcgen05 K2 on the CURRENT stream, for the next
         training `_td_step` (which then skips the packing).  The images depend only on the
@@ -138,9 +159,11 @@ class DQNTrainer(DQNTrainerBaseLightning):
         pack = self._tc_pack_for(key, qd, self.q_network.arena.flat.device)
         if pack is None:
             return False
-        rc = _lib.lib().rb200_dqn_tc_pack(qd, qtd, key[0], key[1], pack.data_ptr(), pack.numel(),
-                                          _lib.cur_stream())
-        _lib.check(rc, "rb200_dqn_tc_pack")
+        if not self._tc_images_current():  # else: the last Adam step already wrote them
+            rc = _lib.lib().rb200_dqn_tc_pack(qd, qtd, key[0], key[1], pack.data_ptr(),
+                                              pack.numel(), _lib.cur_stream())
+            _lib.check(rc, "rb200_dqn_tc_pack")
+            self._tc_images_state = self._tc_state()
         self._tc_prepacked = True
         return True
 
@@ -202,10 +225,11 @@ class DQNTrainer(DQNTrainerBaseLightning):
         if pack is not None:
             rc = _lib.lib().rb200_dqn_td_step_tc(qd, qtd, a, ws["net"].c, pack.data_ptr(),
                                                  pack.numel(),
-                                                 int(self._tc_prepacked and do_backward),
+                                                 int(do_backward and self._tc_images_current()),
                                                  _lib.cur_stream())
             if do_backward:
                 self._tc_prepacked = False
+                self._tc_images_state = self._tc_state()  # packed by this call if they were not
             _lib.check(rc, "rb200_dqn_td_step_tc")
         else:
             rc = _lib.lib().rb200_dqn_td_step(qd, qtd, a, ws["net"].c, _lib.cur_stream())
@@ -240,16 +264,20 @@ class DQNTrainer(DQNTrainerBaseLightning):
         (every loss is a batch mean)."""
         opts = self.optimizers()
         self._td_step(training_batch)
+        tcp = self._tc_pack_in_adam() if self._last_td_call[-1] is not None else None
         if process_group is None:
-            opts[0].fused_step(target=self.q_network_target.arena, tau=self.tau)
+            packed = opts[0].fused_step(target=self.q_network_target.arena, tau=self.tau,
+                                        tc_pack=tcp)
         else:
             from .data_parallel import allreduce_mean_
             from .workspace import reduced_grad
 
             g = reduced_grad(self.q_network.arena)
             scale = allreduce_mean_(g, process_group)
-            opts[0].fused_step(target=self.q_network_target.arena, tau=self.tau, grad=g,
-                               grad_scale=scale)
+            packed = opts[0].fused_step(target=self.q_network_target.arena, tau=self.tau, grad=g,
+                                        grad_scale=scale, tc_pack=tcp)
+        if packed:
+            self._tc_images_state = self._tc_state()
         self.all_batches_processed += 1
         return self._ws["loss"]
 

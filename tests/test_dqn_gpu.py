@@ -301,3 +301,42 @@ def test_dueling_forward_heads_and_state_dict():
     assert torch.equal(q2(x), out)
     qt = q.get_target_network()
     assert torch.equal(qt(x), out)
+
+
+@pytest.mark.parametrize("S,sizes,A", [(128, [256, 128], 16), (10, [24, 12], 3), (36, [300, 130, 20], 9)])
+def test_adam_writes_the_same_weight_images_as_the_pack_kernel(S, sizes, A):
+    """The fused Adam kernel writes the hi/lo tensor-core images of the updated parameters;
+    they must be bit-identical to what rb200_dqn_tc_pack builds from the same parameters."""
+    from reagent_b200 import _lib
+
+    B = 64
+    meta = dict(S=S, A=A, B=B, sizes=sizes, acts=["relu"] * len(sizes), gamma=0.9, tau=0.1,
+                loss="huber", maxq=True, multi_steps=None, time_diff=False, boost=None,
+                double_q=True, lr=1e-2, n_updates=1)
+    torch.manual_seed(S)
+    t = _build_trainer(meta)
+    act = torch.randint(A, (B,))
+    nt = (torch.rand(B, 1) > 0.1).float()
+    b = dict(state=torch.randn(B, S), next_state=torch.randn(B, S), reward=torch.randn(B, 1),
+             time_diff=torch.ones(B, 1), step=None, not_terminal=nt,
+             action=torch.nn.functional.one_hot(act, A).float(),
+             next_action=torch.nn.functional.one_hot(act, A).float() * nt,
+             possible_actions_mask=torch.ones(B, A), possible_next_actions_mask=torch.ones(B, A))
+    batch = _rlt_batch({k: (v.cuda() if v is not None else None) for k, v in b.items()}, meta)
+    for _ in range(2):
+        t.train_batch(batch)
+    assert t._tc_images_current(), "the Adam step should have refreshed the images"
+    qd, qtd, a, wsc, keep, pack = t._last_td_call
+    assert pack is not None
+    torch.cuda.synchronize()
+    by_adam = pack.clone()
+    fresh = torch.zeros_like(pack)
+    rc = _lib.lib().rb200_dqn_tc_pack(t.q_network.arena.desc(), t.q_network_target.arena.desc(), 1, 1,
+                                      fresh.data_ptr(), fresh.numel(), _lib.cur_stream())
+    _lib.check(rc, "rb200_dqn_tc_pack")
+    torch.cuda.synchronize()
+    assert torch.equal(by_adam, fresh)
+    # an in-place torch write to the parameters (what load_state_dict does) invalidates them
+    with torch.no_grad():
+        next(t.q_network.parameters()).mul_(1.0)
+    assert not t._tc_images_current()
