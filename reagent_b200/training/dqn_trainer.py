@@ -142,7 +142,7 @@ class DQNTrainer(DQNTrainerBaseLightning):
         from ..models.arena import ParamArena
 
         qa = self.q_network.arena
-        if type(qa) is not ParamArena or os.environ.get("RB200_NO_ADAM_PACK"):
+        if type(qa) is not ParamArena or os.environ.get("RB200_ADAM_PACK", "0") != "1":
             return None
         pack = self._tc_pack_for((int(bool(self.double_q_learning)), 1), qa.desc(), qa.flat.device)
         return None if pack is None else (pack, 1)

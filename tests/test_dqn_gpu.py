@@ -304,11 +304,12 @@ def test_dueling_forward_heads_and_state_dict():
 
 
 @pytest.mark.parametrize("S,sizes,A", [(128, [256, 128], 16), (10, [24, 12], 3), (36, [300, 130, 20], 9)])
-def test_adam_writes_the_same_weight_images_as_the_pack_kernel(S, sizes, A):
+def test_adam_writes_the_same_weight_images_as_the_pack_kernel(S, sizes, A, monkeypatch):
     """The fused Adam kernel writes the hi/lo tensor-core images of the updated parameters;
     they must be bit-identical to what rb200_dqn_tc_pack builds from the same parameters."""
     from reagent_b200 import _lib
 
+    monkeypatch.setenv("RB200_ADAM_PACK", "1")
     B = 64
     meta = dict(S=S, A=A, B=B, sizes=sizes, acts=["relu"] * len(sizes), gamma=0.9, tau=0.1,
                 loss="huber", maxq=True, multi_steps=None, time_diff=False, boost=None,
