@@ -119,3 +119,35 @@ def test_input_makers_match_reference_formulas():
     oc = PolicyNetworkInputMaker([-2.0, -2.0], [2.0, 2.0])(bc)
     assert oc.action.float_features.tolist() == [[0.0, 1.0], [0.5, -1.0]]
     assert oc.next_action.float_features.tolist() == [[0.0, 0.0], [0.0, 0.0]]
+
+
+def test_dueling_network_layout_cpu():
+    """DuelingQNetwork: reference sub-module names / state_dict keys; all parameters are views
+    into one arena whose compute description is the equivalent plain MLP."""
+    from reagent_b200.models import DuelingQNetwork
+    from reagent_b200.net_builder import Dueling
+    from reagent_b200.core.parameters import NormalizationData, NormalizationParameters as NP
+
+    q = DuelingQNetwork.make_fully_connected(12, 5, [24, 16], ["relu", "tanh"])
+    keys = list(q.state_dict().keys())
+    assert keys == [f"{part}_network.fc.dnn.{i}.0.{w}" for part in ("shared", "advantage", "value")
+                    for i in (0, 1) for w in ("weight", "bias")]
+    ar = q.arena
+    assert ar.dims == [12, 24, 16, 16, 5] and len(ar.acts) == 4
+    base, end = ar.flat.data_ptr(), ar.flat.data_ptr() + 4 * ar.n_true
+    for p in q.parameters():
+        assert base <= p.data_ptr() < end, "every true parameter lives in the arena"
+        assert p._rb200_arena is ar
+    # the two first head layers are consecutive row blocks of the stacked [E x E] layer
+    a0, v0 = q.advantage_network.fc.dnn[0][0].weight, q.value_network.fc.dnn[0][0].weight
+    assert v0.data_ptr() - a0.data_ptr() == 4 * a0.numel()
+    qt = q.get_target_network()
+    assert qt.arena is not ar and torch.equal(qt.arena.flat[: ar.n_true], ar.flat[: ar.n_true])
+    sd = {k: torch.randn_like(v) for k, v in q.state_dict().items()}
+    q.load_state_dict(sd)
+    assert torch.equal(ar.flat[ar.o_wa: ar.o_wa + 5 * 8].view(5, 8), sd["advantage_network.fc.dnn.1.0.weight"])
+    with pytest.raises(AssertionError):
+        DuelingQNetwork.make_fully_connected(12, 5, [24, 15], ["relu", "relu"])  # odd embedding
+    s = NormalizationData({i: NP("CONTINUOUS", mean=0.0, stddev=1.0) for i in range(6)})
+    net = Dueling(sizes=[8, 4], activations=["relu", "relu"]).build_q_network(None, s, 3)
+    assert isinstance(net, DuelingQNetwork) and net.arena.dims == [6, 8, 4, 4, 3]
