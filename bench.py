@@ -365,7 +365,7 @@ def run_ours(args):
                        "step draws one minibatch (host RNG -> pinned -> H2D -> sample kernel) and "
                        "trains on one; the sampler runs one update ahead on a second stream"},
         # sample, (weight images unless Adam wrote them), TD step, weight gradients, Adam+Polyak
-        "gpu_launches": (4 if (not on_tc or os.environ.get("RB200_ADAM_PACK", "0") == "1") else 5) * K,
+        "gpu_launches": (4 if (not on_tc or os.environ.get("RB200_ADAM_PACK", "1") == "1") else 5) * K,
         "clocks": clk,
         "roofline": {"kernel": ("dqn_td_tc_kernel (fused TD target + loss + dZ chain on tcgen05/TMEM)"
                                 if on_tc else

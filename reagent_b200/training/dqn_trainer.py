@@ -127,11 +127,15 @@ class DQNTrainer(DQNTrainerBaseLightning):
         return pack
 
     def _tc_state(self):
-        """What the tensor-core weight images were built from: identity, torch version counter
-        (in-place torch ops, e.g. load_state_dict) and library write epoch of both arenas."""
+        """What the tensor-core weight images were built from: arena identity, the torch version
+        counters of every parameter (in-place torch writes such as load_state_dict bump them;
+        the parameters are views, so the arena's own counter does not see those) and the
+        library's write epoch of both arenas."""
         qa, ta = self.q_network.arena, self.q_network_target.arena
         return (id(qa.flat), qa.flat._version, getattr(qa, "data_epoch", 0),
-                id(ta.flat), ta.flat._version, getattr(ta, "data_epoch", 0))
+                tuple(p._version for p in self.q_network.parameters()),
+                id(ta.flat), ta.flat._version, getattr(ta, "data_epoch", 0),
+                tuple(p._version for p in self.q_network_target.parameters()))
 
     def _tc_images_current(self) -> bool:
         return self.__dict__.get("_tc_images_state") == self._tc_state()
@@ -142,7 +146,7 @@ class DQNTrainer(DQNTrainerBaseLightning):
         from ..models.arena import ParamArena
 
         qa = self.q_network.arena
-        if type(qa) is not ParamArena or os.environ.get("RB200_ADAM_PACK", "0") != "1":
+        if type(qa) is not ParamArena or os.environ.get("RB200_ADAM_PACK", "1") != "1":
             return None
         pack = self._tc_pack_for((int(bool(self.double_q_learning)), 1), qa.desc(), qa.flat.device)
         return None if pack is None else (pack, 1)
