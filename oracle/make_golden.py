@@ -404,6 +404,46 @@ def batch_preprocessor_case(name, seed=0, B=48, S=6, A=4, AD=3):
 
 
 # ---------------------------------------------------------------------------
+# act-time samplers (reagent/gym/policies/samplers/discrete_sampler.py), seeded CPU draws
+# ---------------------------------------------------------------------------
+def sampler_case(name, seed=0, B=40, A=6):
+    ds = ref("reagent.gym.policies.samplers.discrete_sampler")
+    sc = ref("reagent.gym.policies.scorers.discrete_scorer")
+    g = torch.Generator().manual_seed(seed)
+    scores = torch.randn(B, A, generator=g) * 2
+    masked = scores.clone()
+    masked[torch.rand(B, A, generator=g) < 0.25] = -1e10 - 1.0   # invalid actions (DQN convention)
+    masked[torch.arange(B), torch.randint(A, (B,), generator=g)] = 1.0
+    action = torch.nn.functional.one_hot(torch.randint(A, (B,), generator=g), A)
+    arrays = dict(scores=_np(scores), masked=_np(masked), action=_np(action))
+    gr = ds.GreedyActionSampler()
+    out = gr.sample_action(scores)
+    arrays["greedy.action"], arrays["greedy.log_prob"] = _np(out.action), _np(out.log_prob)
+    arrays["greedy.lp_of_action"] = _np(gr.log_prob(scores, action))
+    eg = ds.EpsilonGreedyActionSampler(epsilon=0.3, epsilon_decay=0.5, minimum_epsilon=0.1)
+    torch.manual_seed(seed + 1)
+    out = eg.sample_action(masked)
+    arrays["eps.action"], arrays["eps.log_prob"] = _np(out.action), _np(out.log_prob)
+    torch.manual_seed(seed + 2)
+    arrays["eps.lp_of_action"] = _np(eg.log_prob(masked, action))
+    eg.update(); eg.update(); eg.update()
+    arrays["eps.epsilon_after_3_updates"] = np.array([eg.epsilon])
+    sm = ds.SoftmaxActionSampler(temperature=0.7, temperature_decay=0.5, minimum_temperature=0.2)
+    torch.manual_seed(seed + 3)
+    out = sm.sample_action(scores)
+    arrays["soft.action"], arrays["soft.log_prob"] = _np(out.action), _np(out.log_prob)
+    arrays["soft.lp_of_action"] = _np(sm.log_prob(scores, action))
+    arrays["soft.entropy"] = _np(sm.entropy(scores))
+    sm.update(); sm.update()
+    arrays["soft.temperature_after_2_updates"] = np.array([sm.temperature])
+    one = scores[:1].clone()
+    m1 = torch.tensor([True, False, True, True, False, True])
+    arrays["masked_one"] = _np(sc.apply_possible_actions_mask(one, m1))
+    arrays["mask_one"] = _np(m1)
+    _save(name, arrays, dict(kind="samplers", B=B, A=A, seed=seed))
+
+
+# ---------------------------------------------------------------------------
 # SAC / TD3: torch.randn_like is patched so that the noise draws are recorded
 # ---------------------------------------------------------------------------
 class _NoiseRecorder:
@@ -584,6 +624,7 @@ def main(only=None):
     add(replay_case, "replay_per_big", prioritized=True, cap=4096, n_add=6000, B=256, horizon=1, seed=6, S=8, n_samples=2)
     add(preprocessor_case, "preprocessor_all_types")
     add(batch_preprocessor_case, "batch_preprocessor")
+    add(sampler_case, "act_samplers")
     add(sac_case, "sac_twin_alpha")
     add(sac_case, "sac_single_fixed_alpha", twin=False, learn_alpha=False, seed=3, acts=("tanh", "leaky_relu"))
     add(sac_case, "sac_twin_odd_dims", B=37, S=7, A=2, sizes=(10,), acts=("relu",), seed=5, backprop=False)

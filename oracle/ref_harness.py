@@ -14,7 +14,8 @@ Two glue stubs are needed:
   * `torchrec` -- imported at reagent/core/types.py:22-23, never used on this path;
   * `pytorch_lightning` -- base class only (reagent/training/reagent_lightning_module.py:8,18);
 and `reagent.training` is pre-registered as a bare package so that
-reagent/training/__init__.py:5-24 (imports every trainer) is skipped.
+reagent/training/__init__.py:5-24 (imports every trainer) is skipped; likewise `reagent.gym`
+and `reagent.gym.policies` (their __init__ import the gym environments; `gym` is absent).
 
 All arithmetic that runs is reference + torch code.
 """
@@ -126,6 +127,19 @@ def install_stubs():
     pkg = types.ModuleType("reagent.training")
     pkg.__path__ = [os.path.join(REFERENCE_ROOT, "reagent", "training")]
     sys.modules["reagent.training"] = pkg
+    # `gym` itself: only named in type annotations / isinstance checks of code not run here
+    if "gym" not in sys.modules:
+        spaces = _stub_module("gym.spaces", Discrete=type("Discrete", (), {}),
+                              Box=type("Box", (), {}), MultiDiscrete=type("MultiDiscrete", (), {}))
+        _stub_module("gym", Env=type("Env", (), {}), spaces=spaces)
+    # Same for reagent/gym/__init__.py (imports the gym environments; `gym` is not installed):
+    # only the act-time samplers / scorers below it are used.
+    for sub in ("gym", "gym/policies", "gym/preprocessors", "gym/policies/scorers",
+                "gym/policies/samplers"):
+        name = "reagent." + sub.replace("/", ".")
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "reagent", *sub.split("/"))]
+        sys.modules[name] = pkg
 
 
 def ref(name):

@@ -36,6 +36,9 @@ class TensorDataClass:
     def float(self):
         return self._map(lambda t: t.float())
 
+    def detach(self):
+        return self._map(lambda t: t.detach())
+
     def pin_memory(self):
         return self._map(lambda t: t.pin_memory())
 

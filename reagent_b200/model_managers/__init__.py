@@ -21,8 +21,30 @@ def _device(use_gpu: bool):
     return "cuda"
 
 
+class _DiscretePolicyMixin:
+    def create_policy(self, trainer_module, serving: bool = False, normalization_data_map=None):
+        """Online policy (reagent/model_managers/discrete_dqn_base.py:84-103): greedy over the
+        fused Q-network forward.  Serving modules are out of scope."""
+        if serving:
+            raise NotImplementedError("serving modules are out of scope of reagent_b200")
+        from ..gym.policies import GreedyActionSampler, Policy, discrete_dqn_scorer
+
+        return Policy(scorer=discrete_dqn_scorer(trainer_module.q_network),
+                      sampler=GreedyActionSampler())
+
+
+class _ActorPolicyMixin:
+    def create_policy(self, trainer_module, serving: bool = False, normalization_data_map=None):
+        """reagent/model_managers/actor_critic_base.py:104-118: the actor's forward is the act."""
+        if serving:
+            raise NotImplementedError("serving modules are out of scope of reagent_b200")
+        from ..gym.policies import ActorPolicyWrapper
+
+        return ActorPolicyWrapper(trainer_module.actor_network)
+
+
 @dataclass
-class DiscreteDQN:
+class DiscreteDQN(_DiscretePolicyMixin):
     actions: List[str]
     rl: RLParameters = field(default_factory=RLParameters)
     double_q_learning: bool = True
@@ -47,7 +69,7 @@ class DiscreteDQN:
 
 
 @dataclass
-class DiscreteQRDQN:
+class DiscreteQRDQN(_DiscretePolicyMixin):
     actions: List[str]
     rl: RLParameters = field(default_factory=RLParameters)
     double_q_learning: bool = True
@@ -72,7 +94,7 @@ class DiscreteQRDQN:
 
 
 @dataclass
-class SAC:
+class SAC(_ActorPolicyMixin):
     rl: RLParameters = field(default_factory=RLParameters)
     actor_net_builder: GaussianFullyConnected = field(default_factory=GaussianFullyConnected)
     critic_net_builder: ParametricFullyConnected = field(default_factory=ParametricFullyConnected)
@@ -101,7 +123,7 @@ class SAC:
 
 
 @dataclass
-class TD3:
+class TD3(_ActorPolicyMixin):
     rl: RLParameters = field(default_factory=RLParameters)
     actor_net_builder: ActorFullyConnected = field(default_factory=ActorFullyConnected)
     critic_net_builder: ParametricFullyConnected = field(default_factory=ParametricFullyConnected)
