@@ -439,6 +439,9 @@ void rb200_replay_add_batch_host(const uint8_t* terminal_in_host, int64_t n, int
                                  uint8_t* terminal_store_host, int64_t* state_host);
 /* SumTree.sample(query) on the host heap (sum_tree.py:93-131). */
 int64_t rb200_sumtree_sample_host(const double* tree_host, int32_t depth, double query);
+/* the same walk for queries[pos[0..n)] -> out[0..n) (PER retry check of one stratified draw) */
+void rb200_sumtree_sample_many_host(const double* tree_host, int32_t depth, const double* queries,
+                                    const int64_t* pos, int64_t n, int64_t* out);
 
 #ifdef __cplusplus
 }

@@ -205,6 +205,8 @@ def _declare(lib):
     lib.rb200_sumtree_set_host.argtypes = [_vp, C.c_int32, _vp, _vp, C.c_int64, _vp]
     lib.rb200_sumtree_sample_host.argtypes = [_vp, C.c_int32, C.c_double]
     lib.rb200_sumtree_sample_host.restype = C.c_int64
+    lib.rb200_sumtree_sample_many_host.argtypes = [_vp, C.c_int32, _vp, _vp, C.c_int64, _vp]
+    lib.rb200_sumtree_sample_many_host.restype = None
     lib.rb200_replay_add_batch_host.argtypes = [_vp, C.c_int64, C.c_int64, C.c_int32, _vp, _vp, _vp]
     lib.rb200_replay_add_batch_host.restype = None
     lib.rb200_ac_critic_step.argtypes = [C.POINTER(MlpT), C.POINTER(MlpT), C.POINTER(MlpT),

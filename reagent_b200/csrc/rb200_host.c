@@ -104,6 +104,13 @@ int64_t rb200_sumtree_sample_host(const double* tree, int32_t depth, double quer
   return node;
 }
 
+/* The walk above for the strata `pos[0..n)` of one stratified draw; out[j] = leaf reached by
+ * queries[pos[j]].  One call per update instead of one per candidate stratum. */
+void rb200_sumtree_sample_many_host(const double* tree, int32_t depth, const double* queries,
+                                    const int64_t* pos, int64_t n, int64_t* out) {
+  for (int64_t j = 0; j < n; ++j) out[j] = rb200_sumtree_sample_host(tree, depth, queries[pos[j]]);
+}
+
 /* Validity bookkeeping of N consecutive ReplayBuffer.add() calls with stack_size == 1
  * (reagent/replay_memory/circular_replay_buffer.py:468-522), applied to host arrays.
  * state[0]=add_count, state[1]=transitions in current episode, state[2]=num valid. */

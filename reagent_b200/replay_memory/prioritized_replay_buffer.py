@@ -109,20 +109,31 @@ class PrioritizedReplayBuffer(circular_replay_buffer.ReplayBuffer):
                 i1 = min(B - 1, int(np.ceil(hi * B)) + 1)
                 cand.update(range(i0, i1 + 1))
             cand = sorted(cand)
-            self._cand_cache = (key, cand)
+            pos_arr = np.asarray(cand, dtype=np.int64)
+            hit = np.empty(len(cand), dtype=np.int64)
+            # (numpy's .ctypes accessor costs ~2 us per use: keep the raw addresses)
+            self._cand_cache = (key, cand, pos_arr, hit, pos_arr.ctypes.data, hit.ctypes.data,
+                                tree.heap, tree.heap.ctypes.data)
+            cached = self._cand_cache
+        if not cand:
+            return [], []
+        # one C call walks the tree for every candidate stratum of this draw
+        hit = cached[3]
+        heap_ptr = cached[7] if cached[6] is tree.heap else tree.heap.ctypes.data
+        _lib.lib().rb200_sumtree_sample_many_host(heap_ptr, tree.depth,
+                                                  queries.__array_interface__["data"][0],
+                                                  cached[4], len(cand), cached[5])
+        valid = self._is_index_valid.numpy()
         pos, idxs = [], []
         allowed_attempts = self._max_sample_attempts
-        walk = _lib.lib().rb200_sumtree_sample_host
-        valid = self._is_index_valid
-        for i in cand:
-            index = int(walk(tree.heap.ctypes.data, tree.depth, float(queries[i])))
-            if bool(valid[index]):
+        for i, index in zip(cand, hit.tolist()):
+            if valid[index]:
                 continue
             if allowed_attempts == 0:
                 raise RuntimeError(
                     "Max sample attempts: Tried {} times but only sampled {}"
                     " valid indices. Batch size is {}".format(self._max_sample_attempts, i, B))
-            while not bool(valid[index]) and allowed_attempts > 0:
+            while not valid[index] and allowed_attempts > 0:
                 index = tree.sample()
                 allowed_attempts -= 1
             pos.append(i)
