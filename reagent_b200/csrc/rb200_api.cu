@@ -1,4 +1,3 @@
-#include <stdlib.h>
 // reagent_b200 -- C-ABI plumbing: error text, validation, device queries.
 #include <stdarg.h>
 #include <stdio.h>
@@ -6,14 +5,6 @@
 #include "rb200_common.cuh"
 
 namespace rb200 {
-
-bool pdl_enabled() {
-  // opt-in: measured +3.9 % on the device-timed graph of K updates but -10 % on the per-update
-  // graph replays of FusedDqnStep (profiles/r01_summary.md), so it stays off by default
-  static const bool on = [] { const char* e = getenv("RB200_PDL"); return e && e[0] == '1'; }();
-  return on;
-}
-
 
 static thread_local char g_err[512] = "";
 

@@ -93,41 +93,6 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// ----------------------------------------------------------------------------
-// Programmatic dependent launch: the kernels of one update form a chain on one stream; a
-// kernel launched with launch_pdl() may begin (block scheduling, its own prologue) while its
-// predecessor drains, and must call grid_dependency_wait() before it reads or writes anything
-// the predecessor touches.  Off unless RB200_PDL=1 (see pdl_enabled()): the launches are then
-// ordinary and griddepcontrol.* are no-ops.
-// ----------------------------------------------------------------------------
-__device__ __forceinline__ void grid_dependency_wait() {
-  asm volatile("griddepcontrol.wait;\n" ::: "memory");
-}
-
-// Lets the NEXT kernel of the chain (if launched with launch_pdl) start being scheduled now; it
-// still blocks in its own grid_dependency_wait() until this grid has completed and flushed.
-__device__ __forceinline__ void grid_launch_dependents() {
-  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-}
-
-bool pdl_enabled();
-
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                              cudaStream_t stream, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
-
 // Error plumbing shared by the C-ABI translation units.
 void set_last_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);

@@ -235,10 +235,6 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // everything above (shared-memory clear, barrier init, TMEM allocation) touched no global
-  // memory and may overlap the tail of the previous kernel of the update
-  grid_launch_dependents();
-  grid_dependency_wait();
   if (kTimeline && p.dbg && tid == 0) p.dbg[kQMaxSteps * 8 + blockIdx.x * 4 + 1] = gtime();
 
   // warp-uniform role index (the shuffle lets the compiler keep the role loops in uniform registers)
@@ -825,7 +821,6 @@ extern "C" int rb200_dqn_td_step_tc(const rb200_mlp_t* q_net, const rb200_mlp_t*
   }
   const Mlp q = make_mlp(q_net), qt = make_mlp(q_target);
   const int grid = ceil_div(args->batch, kQR);
-  return check_cuda(launch_pdl(dqn_td_tc_kernel, dim3(grid), dim3(kQThreads), pl.smem_bytes, st, q, qt,
-                               pl.dev),
-                    "dqn_td_tc_kernel launch");
+  dqn_td_tc_kernel<<<grid, kQThreads, pl.smem_bytes, st>>>(q, qt, pl.dev);
+  return check_cuda(cudaGetLastError(), "dqn_td_tc_kernel launch");
 }

@@ -49,8 +49,6 @@ __device__ __forceinline__ void wg_mma(float (&c)[4], const uint32_t (&a)[4], co
 __global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradParams p) {
   __shared__ __align__(16) float zs[2][kWgRows][kWgLd];
   __shared__ __align__(16) float as[2][kWgRows][kWgLd];
-  grid_launch_dependents();
-  grid_dependency_wait();  // dZ / activations come from the TD kernel launched just before
   int li = 0;
   while (li + 1 < p.n_layers && (int)blockIdx.x >= p.L[li + 1].tile_start) ++li;
   const WgradLayer& Ly = p.L[li];
@@ -239,8 +237,6 @@ __device__ __forceinline__ void adam_pack_weight(const TcPackView& pv, long long
 
 __global__ void __launch_bounds__(256) adam_soft_kernel(const AdamDev d) {
   const rb200_adam_args_t& a = d.a;
-  grid_launch_dependents();  // the next update's TD kernel can run its prologue under this one
-  grid_dependency_wait();  // gradient partials come from the kernel launched just before
   // bias corrections in double like torch (Python floats), once per block
   __shared__ long long s_t;
   __shared__ float s_step_size, s_bc2_sqrt;
@@ -363,8 +359,8 @@ extern "C" int rb200_mlp_wgrad(const rb200_mlp_t* net, const float* net_input, i
   }
   for (int l = net->n_layers; l < kMaxLayers; ++l) p.L[l].tile_start = 1 << 30;
   dim3 grid(tiles, splits);
-  return check_cuda(launch_pdl(wgrad_kernel, grid, dim3(kThreads), 0, (cudaStream_t)stream, p),
-                    "wgrad_kernel launch");
+  wgrad_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(p);
+  return check_cuda(cudaGetLastError(), "wgrad_kernel launch");
 }
 
 extern "C" int rb200_grad_reduce(const float* gpart, int32_t splits, int64_t n, float* g,
@@ -404,8 +400,8 @@ extern "C" int rb200_adam_soft_update(const rb200_adam_args_t* a, void* stream) 
   }
   int blocks = (int)((a->n + 255) / 256);
   if (blocks > 148 * 4) blocks = 148 * 4;
-  return check_cuda(launch_pdl(adam_soft_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, d),
-                    "adam_soft_kernel launch");
+  adam_soft_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d);
+  return check_cuda(cudaGetLastError(), "adam_soft_kernel launch");
 }
 
 extern "C" int rb200_soft_update(float* target, const float* source, int64_t n, float tau,
