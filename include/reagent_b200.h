@@ -93,6 +93,9 @@ typedef struct rb200_feature_col {
 
 const char* rb200_last_error(void);
 int rb200_version(void);
+/* sizeof() of an ABI struct by name ("rb200_adam_args_t", ...), -1 if unknown: lets a binding
+ * verify its mirror of the struct against the library it loaded */
+int64_t rb200_abi_sizeof(const char* type_name);
 /* number of SMs / max opt-in smem of the current device (host query helpers) */
 int rb200_device_info(int* sm_count, int* max_smem_optin);
 

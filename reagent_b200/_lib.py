@@ -175,6 +175,8 @@ LIB_PATH = os.environ.get("RB200_LIB") or os.path.join(
 def _declare(lib):
     lib.rb200_last_error.restype = C.c_char_p
     lib.rb200_version.restype = C.c_int
+    lib.rb200_abi_sizeof.argtypes = [C.c_char_p]
+    lib.rb200_abi_sizeof.restype = C.c_int64
     lib.rb200_device_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.rb200_num_row_tiles.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.rb200_dqn_td_step.argtypes = [C.POINTER(MlpT), C.POINTER(MlpT), C.POINTER(DqnArgsT),

@@ -1,5 +1,6 @@
 // reagent_b200 -- C-ABI plumbing: error text, validation, device queries.
 #include <stdarg.h>
+#include <string.h>
 #include <stdio.h>
 
 #include "rb200_common.cuh"
@@ -48,6 +49,24 @@ int validate_mlp(const rb200_mlp_t* d, const char* name) {
 
 extern "C" const char* rb200_last_error(void) { return rb200::g_err; }
 extern "C" int rb200_version(void) { return RB200_VERSION; }
+
+// sizeof() of the structs that cross the C ABI, so that a binding (ctypes / cgo / JNI) can
+// check its own mirror against the library it loaded
+extern "C" int64_t rb200_abi_sizeof(const char* type_name) {
+  if (!type_name) return -1;
+#define RB200_SZ(T) if (!strcmp(type_name, #T)) return (int64_t)sizeof(T)
+  RB200_SZ(rb200_mlp_t);
+  RB200_SZ(rb200_net_ws_t);
+  RB200_SZ(rb200_feature_col_t);
+  RB200_SZ(rb200_dqn_args_t);
+  RB200_SZ(rb200_qrdqn_args_t);
+  RB200_SZ(rb200_ac_args_t);
+  RB200_SZ(rb200_adam_args_t);
+  RB200_SZ(rb200_gather_spec_t);
+  RB200_SZ(rb200_sample_args_t);
+#undef RB200_SZ
+  return -1;
+}
 extern "C" int rb200_device_info(int* sm_count, int* max_smem_optin) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);

@@ -151,3 +151,21 @@ def test_dueling_network_layout_cpu():
     s = NormalizationData({i: NP("CONTINUOUS", mean=0.0, stddev=1.0) for i in range(6)})
     net = Dueling(sizes=[8, 4], activations=["relu", "relu"]).build_q_network(None, s, 3)
     assert isinstance(net, DuelingQNetwork) and net.arena.dims == [6, 8, 4, 4, 3]
+
+
+def test_ctypes_mirrors_match_the_library_struct_sizes():
+    """Every struct that crosses the C ABI: sizeof in the loaded library == sizeof of the ctypes
+    mirror in reagent_b200/_lib.py (a silent mismatch would shift every field after it)."""
+    import ctypes as C
+
+    from reagent_b200 import _lib
+
+    mirrors = {"rb200_mlp_t": _lib.MlpT, "rb200_net_ws_t": _lib.NetWsT,
+               "rb200_feature_col_t": _lib.FeatureColT, "rb200_dqn_args_t": _lib.DqnArgsT,
+               "rb200_qrdqn_args_t": _lib.QrdqnArgsT, "rb200_ac_args_t": _lib.AcArgsT,
+               "rb200_adam_args_t": _lib.AdamArgsT, "rb200_gather_spec_t": _lib.GatherSpecT,
+               "rb200_sample_args_t": _lib.SampleArgsT}
+    lib = _lib.lib()
+    for name, mirror in mirrors.items():
+        assert lib.rb200_abi_sizeof(name.encode()) == C.sizeof(mirror), name
+    assert lib.rb200_abi_sizeof(b"no_such_struct") == -1
