@@ -19,6 +19,18 @@ def pytest_configure(config):
     torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
 
 
+def pytest_sessionstart(session):
+    """The tests need the in-tree library; build it when it is missing and nvcc is here (the
+    product path never does this: `_lib.lib()` fails loudly without the extension)."""
+    import shutil
+    import subprocess
+
+    so = os.path.join(ROOT, "reagent_b200", "libreagent_b200.so")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(so) and os.path.exists(nvcc):
+        subprocess.run(["bash", os.path.join(ROOT, "reagent_b200", "csrc", "build.sh")], check=True)
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
 
