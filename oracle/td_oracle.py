@@ -68,9 +68,13 @@ def mlp(net: Net, x: torch.Tensor) -> torch.Tensor:
     q = value + (advantage - mean over the non-batch dims of advantage)."""
     if net.get("kind") == "dueling":
         shared = mlp(net["shared"], x)
-        value = mlp(net["val"], shared)
-        raw_adv = mlp(net["adv"], shared)
-        return value + (raw_adv - raw_adv.mean(dim=1, keepdim=True))
+        value = mlp(net["val"], shared)          # (B, N) -- N = 1 without atoms
+        raw_adv = mlp(net["adv"], shared)        # (B, A*N)
+        B, N = value.shape
+        adv = raw_adv.view(B, -1, N)
+        # mean over ALL non-batch dims (actions and atoms), dueling_q_network.py:98-101
+        q = value.view(B, 1, N) + (adv - adv.mean(dim=(1, 2), keepdim=True))
+        return q.reshape(B, -1)
     for w, b, a in zip(net["W"], net["b"], net["act"]):
         x = _ACT[a](F.linear(x, w, b))
     return x
