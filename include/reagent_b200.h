@@ -331,7 +331,24 @@ typedef struct rb200_adam_args {
   void* tc_pack_ws;            /* the scratch buffer of rb200_dqn_td_step_tc */
   int64_t tc_pack_ws_bytes;
   int32_t tc_do_backward;      /* also the transposed images of the backward */
+  /* Optional: data-parallel gradient exchange FUSED into this launch (dp_world > 1), replacing
+   * rb200_grad_reduce + an NCCL all-reduce + this kernel by one kernel per rank.  Every rank
+   * launches the same grid; block b of every rank (1) sums its slice of its own split-K
+   * partials, (2) PUSHES the slice into every peer's receive buffer with peer-to-peer stores
+   * over NVLink and raises a per-block flag there, (3) waits for the W-1 flags of its own
+   * slice, (4) adds the W slices in rank order -- every rank computes the bit-identical global
+   * gradient -- scales by grad_scale (1/W) and runs Adam / Polyak / packing as above.
+   * dp_recv[r] / dp_flags[r] are DEVICE arrays of W peer-mapped pointers (rb200_dp_ipc_open):
+   *   recv  of rank r: float    [2][W][dp_stride]      (parity of the step, source rank)
+   *   flags of rank r: uint32_t [2][W][dp_max_blocks]  zero-initialised once
+   * Two parities suffice: a rank cannot finish step k+1 before every peer has finished step k. */
+  int32_t dp_world, dp_rank;
+  float* const* dp_recv;
+  uint32_t* const* dp_flags;
+  int64_t dp_stride;           /* >= n */
+  int32_t dp_max_blocks;       /* >= the grid this call launches (rb200_adam_blocks(n)) */
 } rb200_adam_args_t;
+int rb200_adam_blocks(int64_t n);
 int rb200_adam_soft_update(const rb200_adam_args_t* a, void* stream);
 /* stand-alone Polyak update (SoftUpdate.step when not fused) */
 int rb200_soft_update(float* target, const float* source, int64_t n, float tau,
@@ -424,6 +441,21 @@ int rb200_replay_sample(const rb200_sample_args_t* args, void* stream);
  * counts [ceil(cap/256)], offsets [ceil(cap/256)+1] */
 int rb200_valid_index_build(const uint8_t* valid, int64_t capacity, int32_t* counts,
                             int32_t* offsets, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Peer-memory plumbing of the fused data-parallel step (one process per GPU).  The    */
+/* reference has no collective on this path (docs/distributed.rst:12-22 states the     */
+/* intent: synchronous data parallelism with a gradient all-reduce).                   */
+/*   rb200_dp_alloc      cudaMalloc'ed, zero-filled, IPC-exportable device buffer      */
+/*   rb200_dp_ipc_handle 64-byte handle of such a buffer (cudaIpcGetMemHandle)          */
+/*   rb200_dp_ipc_open   map a peer process's buffer into this one (enables peer access)*/
+/* ------------------------------------------------------------------------- */
+#define RB200_IPC_HANDLE_BYTES 64
+int rb200_dp_alloc(int64_t bytes, void** out_ptr);
+int rb200_dp_free(void* ptr);
+int rb200_dp_ipc_handle(void* ptr, unsigned char* handle_out_host);
+int rb200_dp_ipc_open(const unsigned char* handle_host, void** out_ptr);
+int rb200_dp_ipc_close(void* ptr);
 
 /* ---- host-side helpers (plain C, no CUDA; pointers are HOST memory) -------- */
 /* MT19937 with CPython's exact stream: fills out[i] = lo[i] + (hi[i]-lo[i])*random()

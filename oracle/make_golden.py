@@ -305,6 +305,87 @@ def replay_case(name, *, prioritized, cap, n_add, B, horizon=1, stack=1, gamma=0
 
 
 # ---------------------------------------------------------------------------
+# InputMakers on a sampled reference batch (the path bench.py times):
+# reagent/gym/preprocessors/trainer_preprocessor.py:100-227, reagent/training/utils.py:13-29
+# ---------------------------------------------------------------------------
+def inputmaker_case(name, *, prioritized, continuous, cap, n_add, B, horizon=1, gamma=0.9, S=6,
+                    A=4, seed=0, p_term=0.08, with_masks=False, n_samples=2):
+    import random
+    crb = ref("reagent.replay_memory.circular_replay_buffer")
+    prb = ref("reagent.replay_memory.prioritized_replay_buffer")
+    tp = ref("reagent.gym.preprocessors.trainer_preprocessor")
+    rng = np.random.RandomState(seed)
+    st = dict(observation=rng.randn(n_add, S).astype(np.float32),
+              reward=rng.randn(n_add).astype(np.float32),
+              terminal=(rng.rand(n_add) < p_term),
+              priority=rng.uniform(0.1, 10.0, size=n_add),
+              log_prob=(-rng.rand(n_add) * 2).astype(np.float32))
+    low = high = None
+    if continuous:
+        low = np.linspace(-2.0, 0.0, A).astype(np.float32)
+        high = np.linspace(1.0, 3.0, A).astype(np.float32)
+        st["action"] = (low + (high - low) * rng.rand(n_add, A)).astype(np.float32)
+    else:
+        st["action"] = rng.randint(0, A, size=n_add).astype(np.int64)
+    if with_masks:
+        m = (rng.rand(n_add, A) > 0.3)
+        m[np.arange(n_add), rng.randint(0, A, n_add)] = True
+        st["possible_actions_mask"] = m.astype(np.float32)
+    cls = prb.PrioritizedReplayBuffer if prioritized else crb.ReplayBuffer
+    rb = cls(stack_size=1, replay_capacity=cap, batch_size=B, update_horizon=horizon, gamma=gamma)
+    keys = ["observation", "action", "reward", "terminal", "log_prob"]
+    if with_masks:
+        keys.append("possible_actions_mask")
+    if prioritized:
+        keys.append("priority")
+    for t in range(n_add):
+        kw = {}
+        for k in keys:
+            v = st[k][t]
+            if k == "terminal":
+                v = bool(v)
+            elif k == "priority":
+                v = float(v)
+            elif k == "action" and not continuous:
+                v = int(v)
+            elif np.ndim(v) == 0:
+                v = float(v)
+            kw[k] = v
+        rb.add(**kw)
+    arrays = {f"stream.{k}": st[k] for k in keys}
+    if continuous:
+        arrays["action_low"], arrays["action_high"] = low, high
+        maker = tp.PolicyNetworkInputMaker(low, high)
+    else:
+        maker = tp.DiscreteDqnInputMaker(num_actions=A)
+    random.seed(seed + 200)
+    torch.manual_seed(seed + 200)
+    np.random.seed(seed + 200)
+    for s_i in range(n_samples):
+        raw = rb.sample_transition_batch(batch_size=B)
+        out = maker(raw)
+        arrays[f"sample{s_i}.indices"] = _np(raw.indices)
+        arrays[f"sample{s_i}.terminal"] = _np(raw.terminal)
+        got = dict(state=out.state.float_features, next_state=out.next_state.float_features,
+                   reward=out.reward, not_terminal=out.not_terminal,
+                   action_probability=out.extras.action_probability)
+        if continuous:
+            got["action"] = out.action.float_features
+            got["next_action"] = out.next_action.float_features
+        else:
+            got.update(action=out.action, next_action=out.next_action,
+                       possible_actions_mask=out.possible_actions_mask,
+                       possible_next_actions_mask=out.possible_next_actions_mask)
+        assert out.step is None and out.time_diff is None
+        for k, v in got.items():
+            arrays[f"sample{s_i}.{k}"] = _np(v)
+    meta = dict(kind="inputmaker", prioritized=prioritized, continuous=continuous, cap=cap,
+                n_add=n_add, B=B, horizon=horizon, gamma=gamma, S=S, A=A, seed=seed,
+                with_masks=with_masks, n_samples=n_samples, keys=keys)
+    _save(name, arrays, meta)
+
+
+# ---------------------------------------------------------------------------
 # dense preprocessor
 # ---------------------------------------------------------------------------
 def preprocessor_case(name, seed=0, B=64):
@@ -637,6 +718,10 @@ def main(only=None):
     add(replay_case, "replay_per_h1", prioritized=True, cap=100, n_add=90, B=32, seed=4)
     add(replay_case, "replay_per_h3_wrap_zero", prioritized=True, cap=64, n_add=200, B=48, horizon=3, seed=5, zero_priority_every=7, p_term=0.02)
     add(replay_case, "replay_per_big", prioritized=True, cap=4096, n_add=6000, B=256, horizon=1, seed=6, S=8, n_samples=2)
+    add(inputmaker_case, "inputmaker_dqn_uniform", prioritized=False, continuous=False, cap=128, n_add=300, B=32)
+    add(inputmaker_case, "inputmaker_dqn_per_masks", prioritized=True, continuous=False, cap=256, n_add=200, B=48, seed=1, with_masks=True, horizon=3, gamma=0.95)
+    add(inputmaker_case, "inputmaker_policy_uniform", prioritized=False, continuous=True, cap=128, n_add=250, B=32, A=3, seed=2)
+    add(inputmaker_case, "inputmaker_policy_per_h3", prioritized=True, continuous=True, cap=256, n_add=400, B=40, A=5, seed=3, horizon=3, gamma=0.97)
     add(preprocessor_case, "preprocessor_all_types")
     add(batch_preprocessor_case, "batch_preprocessor")
     add(sampler_case, "act_samplers")

@@ -99,6 +99,52 @@ class ReplayOracle:
             for i in range(min(self.ep, self.h)):
                 self.valid[(cur - i) % self.cap] = True
 
+    def bulk_fill(self, stream):
+        """State after `add(**row)` for every row of `stream` (dict of arrays, n <= capacity
+        rows, empty buffer) without the per-row python loop.  The sum tree is bit-identical to
+        n sequential SumTree.set calls (sum_tree.py:164-189): filling leaves 0..n-1 of an empty
+        tree in order makes every inner node the left-to-right sequential fp64 sum of its
+        leaves, which is what np.cumsum (strictly sequential accumulate) computes.
+        Pinned against the sequential path in tests/test_oracle_golden.py."""
+        n = len(stream["terminal"])
+        assert self.add_count == 0 and n <= self.cap
+        self.store = {}
+        for k, v in stream.items():
+            if k == "priority":
+                continue
+            a = np.asarray(v)
+            dt = np.float32 if a.dtype == np.float64 else a.dtype
+            self.store[k] = np.zeros((self.cap,) + a.shape[1:], dtype=dt)
+            self.store[k][:n] = a
+        term = np.asarray(stream["terminal"]).astype(bool)
+        # validity (circular_replay_buffer.py:491-522): position in the episode >= horizon
+        # steps before the episode's current end, or within the last `horizon` of a finished one
+        ends = np.flatnonzero(term)
+        ep_start = np.zeros(n, dtype=np.int64)
+        starts = np.concatenate([[0], ends + 1])
+        for a0, a1 in zip(starts, np.concatenate([ends + 1, [n]])):
+            ep_start[a0:a1] = a0
+        nxt_end = np.full(n, -1, dtype=np.int64)  # index of the terminal closing this episode
+        for a0, a1 in zip(starts, np.concatenate([ends + 1, [n]])):
+            if a1 - 1 < n and a1 >= 1 and a1 - 1 >= a0 and term[a1 - 1]:
+                nxt_end[a0:a1] = a1 - 1
+        i = np.arange(n)
+        last = np.where(nxt_end >= 0, nxt_end, n - 1)  # last written slot of the episode
+        closed = nxt_end >= 0
+        # open episode: slot i is valid once i + h <= last written index of that episode
+        self.valid[:] = False
+        self.valid[:n] = np.where(closed, True, i + self.h <= last)
+        self.add_count = n
+        self.ep = 0 if (n and term[n - 1]) else int(n - ep_start[n - 1]) if n else 0
+        if self.tree is not None:
+            pr = np.zeros(len(self.tree.nodes[-1]))
+            pr[:n] = np.asarray(stream["priority"], dtype=np.float64)
+            assert (pr >= 0).all()
+            for l, lvl in enumerate(self.tree.nodes):
+                width = len(pr) // len(lvl)
+                lvl[:] = np.cumsum(pr.reshape(len(lvl), width), axis=1)[:, -1]
+            self.tree.max_recorded_priority = max(1.0, float(pr.max()))
+
     def sample_index_batch(self, B):
         if self.tree is None:  # :589-603
             valid = torch.from_numpy(self.valid).nonzero().squeeze(1)

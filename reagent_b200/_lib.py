@@ -89,6 +89,12 @@ class AdamArgsT(C.Structure):
         ("tc_pack_ws", _vp),
         ("tc_pack_ws_bytes", C.c_int64),
         ("tc_do_backward", C.c_int32),
+        ("dp_world", C.c_int32),
+        ("dp_rank", C.c_int32),
+        ("dp_recv", _vp),
+        ("dp_flags", _vp),
+        ("dp_stride", C.c_int64),
+        ("dp_max_blocks", C.c_int32),
     ]
 
 
@@ -223,6 +229,12 @@ def _declare(lib):
     lib.rb200_grad_reduce.argtypes = [_vp, C.c_int32, C.c_int64, _vp, _vp]
     lib.rb200_adam_soft_update.argtypes = [C.POINTER(AdamArgsT), _vp]
     lib.rb200_soft_update.argtypes = [_vp, _vp, C.c_int64, C.c_float, C.c_float, _vp]
+    lib.rb200_adam_blocks.argtypes = [C.c_int64]
+    lib.rb200_dp_alloc.argtypes = [C.c_int64, C.POINTER(_vp)]
+    lib.rb200_dp_free.argtypes = [_vp]
+    lib.rb200_dp_ipc_handle.argtypes = [_vp, _vp]
+    lib.rb200_dp_ipc_open.argtypes = [_vp, C.POINTER(_vp)]
+    lib.rb200_dp_ipc_close.argtypes = [_vp]
 
 
 def lib():

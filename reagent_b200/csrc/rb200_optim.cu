@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(256) adam_soft_kernel(const AdamDev d) {
   const float wd = (float)a.weight_decay;
   const long long n = a.n;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    // split-K partials: loads issued 8 at a time, summed in slab order (deterministic)
+  // split-K partials: loads issued 8 at a time, summed in slab order (deterministic)
+  auto local_grad = [&](long long i) {
     float g = 0.f;
     for (int s0 = 0; s0 < a.splits; s0 += 8) {
       float part[8];
@@ -270,6 +270,47 @@ __global__ void __launch_bounds__(256) adam_soft_kernel(const AdamDev d) {
 #pragma unroll
       for (int u = 0; u < 8; ++u)
         if (s0 + u < a.splits) g = (s0 + u == 0) ? part[u] : g + part[u];
+    }
+    return g;
+  };
+  const int W = a.dp_world;
+  const float* dp_mine = nullptr;
+  if (W > 1) {
+    // ---- fused gradient exchange over NVLink peer memory (see rb200_adam_args_t) ----
+    const unsigned par = (unsigned)(t & 1);
+    const size_t slot = ((size_t)par * W + a.dp_rank) * (size_t)a.dp_stride;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const float g = local_grad(i);
+      for (int r = 0; r < W; ++r) a.dp_recv[r][slot + i] = g;  // own copy included
+    }
+    __syncthreads();
+    const size_t fslot = ((size_t)par * W) * a.dp_max_blocks + blockIdx.x;
+    if ((int)threadIdx.x < W && (int)threadIdx.x != a.dp_rank) {
+      __threadfence_system();  // this block's pushes (ordered by the barrier) before the flag
+      uint32_t* f = a.dp_flags[threadIdx.x] + fslot + (size_t)a.dp_rank * a.dp_max_blocks;
+      asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(f), "r"((uint32_t)t) : "memory");
+      // and wait for that peer's push of the same slice (it never waits before pushing)
+      const uint32_t* w = a.dp_flags[a.dp_rank] + fslot + (size_t)threadIdx.x * a.dp_max_blocks;
+      unsigned long long t0 = 0, now = 0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(w) : "memory");
+        if (v == (uint32_t)t) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > 4000000000ull) __trap();  // 4 s: a lost peer fails the step, never hangs
+      }
+    }
+    __syncthreads();
+    dp_mine = a.dp_recv[a.dp_rank] + (size_t)par * W * (size_t)a.dp_stride;
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float g;
+    if (W > 1) {
+      g = __ldcg(dp_mine + i);
+      for (int r = 1; r < W; ++r) g += __ldcg(dp_mine + (size_t)r * a.dp_stride + i);
+    } else {
+      g = local_grad(i);
     }
     g *= a.grad_scale;
     float p = a.params[i];
@@ -398,10 +439,24 @@ extern "C" int rb200_adam_soft_update(const rb200_adam_args_t* a, void* stream) 
     d.pv.has_bwd = im.has_bwd;
     d.pv.pack = static_cast<float*>(a->tc_pack_ws);
   }
-  int blocks = (int)((a->n + 255) / 256);
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  const int blocks = rb200_adam_blocks(a->n);
+  if (a->dp_world > 1) {
+    if (!a->dp_recv || !a->dp_flags || a->dp_rank < 0 || a->dp_rank >= a->dp_world ||
+        a->dp_world > 256 || a->dp_stride < a->n || a->dp_max_blocks < blocks) {
+      set_last_error("rb200_adam_soft_update: bad data-parallel exchange arguments"); return RB200_E_INVALID;
+    }
+  } else {
+    d.a.dp_world = 1;
+  }
   adam_soft_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d);
   return check_cuda(cudaGetLastError(), "adam_soft_kernel launch");
+}
+
+// grid of rb200_adam_soft_update for an arena of n floats (all blocks co-resident on 148 SMs)
+extern "C" int rb200_adam_blocks(int64_t n) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  return blocks < 1 ? 1 : blocks;
 }
 
 extern "C" int rb200_soft_update(float* target, const float* source, int64_t n, float tau,

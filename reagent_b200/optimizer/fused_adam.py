@@ -68,10 +68,13 @@ class FusedAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def fused_step(self, target: Optional[ParamArena] = None, tau: float = 0.0,
                    grad: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
-                   exp_out: Optional[torch.Tensor] = None, tc_pack=None):
+                   exp_out: Optional[torch.Tensor] = None, tc_pack=None, dp=None):
         """Adam step (+ Polyak update of `target` with the NEW parameters when given).
         `tc_pack = (pack_tensor, do_backward)`: also write the tensor-core weight images of the
-        updated network and target for the next rb200_dqn_td_step_tc (needs `target`)."""
+        updated network and target for the next rb200_dqn_td_step_tc (needs `target`).
+        `dp`: a training.data_parallel.P2PExchange -- the gradient exchange between the ranks is
+        fused into this launch (peer-to-peer stores over NVLink, summed in rank order, scaled
+        by 1/world); `grad` must then be this rank's own split-K partials (the default)."""
         self._ensure_state()
         a = self.arena
         if grad is None:
@@ -107,6 +110,13 @@ class FusedAdam(torch.optim.Optimizer):
             args.tau = 0.0
             args.one_minus_tau = 1.0
         args.exp_out = None if exp_out is None else exp_out.data_ptr()
+        args.dp_world = 1
+        if dp is not None and dp.world > 1:
+            recv, flags, stride, maxb = dp.slice_for(id(self), a.n)
+            args.dp_world, args.dp_rank = dp.world, dp.rank
+            args.dp_recv, args.dp_flags = recv.data_ptr(), flags.data_ptr()
+            args.dp_stride, args.dp_max_blocks = stride, maxb
+            args.grad_scale = float(grad_scale) / dp.world
         desc = None
         if tc_pack is not None and target is not None:
             import ctypes as C

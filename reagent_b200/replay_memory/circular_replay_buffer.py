@@ -641,21 +641,36 @@ class ReplayBuffer:
         args.action_onehot = action.data_ptr()
         args.next_action_onehot = next_action.data_ptr()
         prob = None
+        ns = 0
+
+        def spec(key, name, which, width):
+            nonlocal ns
+            out = self._alloc(name, B, width)
+            args.specs[ns].src = self._store[key].data_ptr()
+            args.specs[ns].dst = out.data_ptr()
+            args.specs[ns].row_bytes = 4 * width
+            args.specs[ns].which = which
+            ns += 1
+            return out
+
         if "log_prob" in self._store:
-            lp = self._alloc("log_prob", B, 1)
-            args.n_specs = 1
-            args.specs[0].src = self._store["log_prob"].data_ptr()
-            args.specs[0].dst = lp.data_ptr()
-            args.specs[0].row_bytes = 4
-            args.specs[0].which = 0
-            prob = lp
+            prob = spec("log_prob", "log_prob", 0, 1)
+        # DiscreteDqnInputMaker :131-139: masks come from the `possible_actions_mask` extra
+        # (and its `next_` twin) when the buffer stores one, else ones
+        pam = pnam = self._ones(B, num_actions)
+        if "possible_actions_mask" in self._store:
+            md = self._key_to_replay_elem["possible_actions_mask"].metadata
+            if md.dtype != np.float32 or md.shape != (num_actions,):
+                raise NotImplementedError("possible_actions_mask must be float32 [num_actions]")
+            pam = spec("possible_actions_mask", "possible_actions_mask", 0, num_actions)
+            pnam = spec("possible_actions_mask", "possible_next_actions_mask", 1, num_actions)
+        args.n_specs = ns
         _lib.check(_lib.lib().rb200_replay_sample(args, _lib.cur_stream()), "rb200_replay_sample")
-        ones = self._ones(B, num_actions)
         batch = rlt.DiscreteDqnInput(
             state=rlt.FeatureData(t["state"]), next_state=rlt.FeatureData(t["next_state"]),
             reward=t["reward"], time_diff=None, step=t["step"], not_terminal=t["not_terminal"],
-            action=action, next_action=next_action, possible_actions_mask=ones,
-            possible_next_actions_mask=ones,
+            action=action, next_action=next_action, possible_actions_mask=pam,
+            possible_next_actions_mask=pnam,
             extras=rlt.ExtraData(action_probability=None if prob is None else prob.exp()))
         batch.indices = t["indices"]
         batch.sampling_probabilities = t.get("sampling_probabilities")
@@ -685,13 +700,22 @@ class ReplayBuffer:
         args.action_low = lo.data_ptr()
         args.action_high = hi.data_ptr()
         args.train_low, args.train_high = CONTINUOUS_TRAINING_ACTION_RANGE
+        prob = None
+        if "log_prob" in self._store:  # extras.action_probability = log_prob.exp() (:206)
+            prob = self._alloc("log_prob", B, 1)
+            args.n_specs = 1
+            args.specs[0].src = self._store["log_prob"].data_ptr()
+            args.specs[0].dst = prob.data_ptr()
+            args.specs[0].row_bytes = 4
+            args.specs[0].which = 0
         _lib.check(_lib.lib().rb200_replay_sample(args, _lib.cur_stream()), "rb200_replay_sample")
         batch = rlt.PolicyNetworkInput(
             state=rlt.FeatureData(t["state"]), next_state=rlt.FeatureData(t["next_state"]),
             reward=t["reward"], time_diff=None, step=t["step"], not_terminal=t["not_terminal"],
             action=rlt.FeatureData(action), next_action=rlt.FeatureData(next_action),
-            extras=rlt.ExtraData())
+            extras=rlt.ExtraData(action_probability=None if prob is None else prob.exp()))
         batch.indices = t["indices"]
+        batch.sampling_probabilities = t.get("sampling_probabilities")
         return batch
 
     def get_transition_elements(self):

@@ -264,22 +264,16 @@ class DQNTrainer(DQNTrainerBaseLightning):
         """Fast path: one full update in 3 launches, Polyak fused into the Adam kernel.
         Same arithmetic as driving train_step_gen with reagent_b200.training.loop.
         With `process_group` (data parallel, one rank per GPU, equal shards): the flat
-        gradient is summed over ranks by ONE all-reduce and scaled by 1/world before Adam
-        (every loss is a batch mean)."""
+        gradient is summed over ranks and scaled by 1/world before Adam (every loss is a batch
+        mean) -- inside the Adam kernel over NVLink peer memory when
+        data_parallel.enable_p2p(group) was called, else by ONE NCCL all-reduce."""
         opts = self.optimizers()
         self._td_step(training_batch)
         tcp = self._tc_pack_in_adam() if self._last_td_call[-1] is not None else None
-        if process_group is None:
-            packed = opts[0].fused_step(target=self.q_network_target.arena, tau=self.tau,
-                                        tc_pack=tcp)
-        else:
-            from .data_parallel import allreduce_mean_
-            from .workspace import reduced_grad
+        from .data_parallel import dp_fused_step
 
-            g = reduced_grad(self.q_network.arena)
-            scale = allreduce_mean_(g, process_group)
-            packed = opts[0].fused_step(target=self.q_network_target.arena, tau=self.tau, grad=g,
-                                        grad_scale=scale, tc_pack=tcp)
+        packed = dp_fused_step(opts[0], self.q_network.arena, process_group,
+                               target=self.q_network_target.arena, tau=self.tau, tc_pack=tcp)
         if packed:
             self._tc_images_state = self._tc_state()
         self.all_batches_processed += 1

@@ -197,16 +197,10 @@ class QRDQNTrainer(DQNTrainerBaseLightning):
                     process_group=None):
         opts = self.optimizers()
         self._qr_step(training_batch)
-        if process_group is None:
-            opts[0].fused_step(target=self.q_network_target.arena, tau=self.tau)
-        else:
-            from .data_parallel import allreduce_mean_
-            from .workspace import reduced_grad
+        from .data_parallel import dp_fused_step
 
-            g = reduced_grad(self.q_network.arena)
-            scale = allreduce_mean_(g, process_group)
-            opts[0].fused_step(target=self.q_network_target.arena, tau=self.tau, grad=g,
-                               grad_scale=scale)
+        dp_fused_step(opts[0], self.q_network.arena, process_group,
+                      target=self.q_network_target.arena, tau=self.tau)
         self.all_batches_processed += 1
         return self._ws["loss"]
 

@@ -187,13 +187,6 @@ class SACTrainer(ActorCriticBase):
         return closs, aloss
 
     def _dp_step(self, opt, arena, target, process_group, exp_out=None):
-        if process_group is None:
-            opt.fused_step(target=target, tau=self.tau, exp_out=exp_out)
-            return
-        from .data_parallel import allreduce_mean_
-        from .workspace import reduced_grad
+        from .data_parallel import dp_fused_step
 
-        g = reduced_grad(arena)
-        scale = allreduce_mean_(g, process_group)
-        opt.fused_step(target=target, tau=self.tau, grad=g, exp_out=exp_out,
-                       grad_scale=scale)
+        dp_fused_step(opt, arena, process_group, target=target, tau=self.tau, exp_out=exp_out)

@@ -125,13 +125,6 @@ class TD3Trainer(ActorCriticBase):
         return closs, aloss
 
     def _dp_step(self, opt, arena, target, process_group):
-        if process_group is None:
-            opt.fused_step(target=target, tau=self.tau)
-            return
-        from .data_parallel import allreduce_mean_
-        from .workspace import reduced_grad
+        from .data_parallel import dp_fused_step
 
-        g = reduced_grad(arena)
-        scale = allreduce_mean_(g, process_group)
-        opt.fused_step(target=target, tau=self.tau, grad=g,
-                       grad_scale=scale)
+        dp_fused_step(opt, arena, process_group, target=target, tau=self.tau)

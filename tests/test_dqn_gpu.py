@@ -129,9 +129,28 @@ def test_dqn_fast_path_matches_reference(name, path, monkeypatch):
     _check_against_golden(t, arrays, meta, losses)
 
 
+def _record(name, **kv):
+    """Measurements the tolerances below are derived from (kept with the round's GPU logs)."""
+    import json, os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "test_measurements.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **kv}) + "\n")
+
+
+# Bounds of test_dqn_config2_matches_oracle, each 10x what was measured on B200 (round 2,
+# gpurun_out/test_measurements.jsonl): rows whose ReLU pattern differs from the oracle's (a
+# hidden unit within ~5e-6 of 0 flips), and post-Adam elements off by more than 1e-5.
+CONFIG2_MAX_FLIPPED_ROWS = 60
+CONFIG2_MAX_ADAM_OUTLIER_FRAC = 0.02
+
+
 @pytest.mark.parametrize("path", K2_PATHS)
 def test_dqn_config2_matches_oracle(path, monkeypatch):
-    """BASELINE config 2 shapes: S=128, A=16, B=4096, [256,128] relu, double-Q, huber."""
+    """BASELINE config 2 shapes: S=128, A=16, B=4096, [256,128] relu, double-Q, huber.
+    1e-5 (north star) on everything computed on rows whose activation pattern equals the
+    oracle's; the number of other rows is asserted small; the weight gradient is compared at
+    1e-5 with exactly those rows' contributions exchanged."""
     _select_k2(monkeypatch, path)
     meta = dict(S=128, A=16, B=4096, sizes=[256, 128], acts=["relu", "relu"], gamma=0.99,
                 tau=0.005, loss="huber", maxq=True, multi_steps=None, time_diff=False,
@@ -158,6 +177,28 @@ def test_dqn_config2_matches_oracle(path, monkeypatch):
     adam = O.AdamState(O.net_params(qo), lr=meta["lr"])
     gb = {k: (v.cuda() if v is not None else None) for k, v in b.items()}
     batch = _rlt_batch(gb, meta)
+
+    # ---- per-row view of the first update on the oracle side: z_l, h_l, dLoss/dz_l ----
+    def oracle_rows():
+        hs, zs = [], []
+        x = b["state"]
+        for w, bb, a in zip(qo["W"], qo["b"], qo["act"]):
+            z = torch.nn.functional.linear(x, w, bb)
+            z.retain_grad()
+            zs.append(z)
+            x = torch.relu(z) if a == "relu" else z
+            hs.append(x)
+        _, aux = O.dqn_td_loss(qo, qt, b, gamma=meta["gamma"], double_q=True, maxq=True, loss="huber")
+        q_sel = torch.sum(hs[-1] * b["action"], 1, keepdim=True)
+        loss = torch.nn.functional.smooth_l1_loss(q_sel, aux["target"])
+        loss.backward()
+        dz = [z.grad.detach().clone() for z in zs]
+        for p_ in O.net_params(qo):
+            p_.grad = None
+        return [h.detach() for h in hs], dz
+
+    h_ref, dz_ref = oracle_rows()
+    flipped = None
     for it in range(meta["n_updates"]):
         lo, grads, aux = O.dqn_update(qo, qt, adam, b, gamma=meta["gamma"], tau=meta["tau"],
                                       double_q=True, maxq=True, loss="huber")
@@ -166,17 +207,50 @@ def test_dqn_config2_matches_oracle(path, monkeypatch):
         if it == 0:
             assert torch.equal(t._ws["next_idx"].cpu().long(), aux["next_idx"].reshape(-1))
             assert G.rel_err(t._ws["td_target"], aux["target"].reshape(-1)) < TOL
-            for i, g in enumerate(t.q_network_grads()):
-                G.grad_close(g, grads[i], f"grad {i}")
+            assert G.rel_err(t._ws["scores"], aux["all_q"]) < TOL
+            net = t._ws["net"]
+            h_gpu = [h.cpu() for h in net.hidden]
+            dz_gpu = [z.cpu() for z in net.dz]
+            same = torch.ones(B, dtype=torch.bool)
+            for l in range(2):
+                same &= ((h_gpu[l] > 0) == (h_ref[l] > 0)).all(dim=1)
+            flipped = int((~same).sum())
+            assert flipped <= CONFIG2_MAX_FLIPPED_ROWS, flipped
+            for l in range(2):  # saved activations: 1e-5 everywhere (a flip moves h by < 1e-5)
+                assert G.rel_err(h_gpu[l], h_ref[l]) < TOL, ("hidden", l)
+            for l in range(3):  # dLoss/dz per row: 1e-5 on the rows with the oracle's pattern
+                assert G.rel_err(dz_gpu[l][same], dz_ref[l][same]) < TOL, ("dz", l)
+            # weight gradients at 1e-5: the oracle's, with the flipped rows' contributions
+            # replaced by what follows from the GPU's own dz on those rows
+            inputs = [b["state"]] + h_ref[:2]
+            g_gpu = t.q_network_grads()
+            worst = 0.0
+            for l in range(3):
+                dzm = dz_ref[l].clone()
+                dzm[~same] = dz_gpu[l][~same]
+                gw = dzm.double().t() @ inputs[l].double()
+                gb_ = dzm.double().sum(0)
+                ew, eb = G.rel_err(g_gpu[2 * l], gw), G.rel_err(g_gpu[2 * l + 1], gb_)
+                worst = max(worst, ew, eb)
+                assert ew < TOL and eb < TOL, ("wgrad", l, ew, eb)
+            # and against the unmodified oracle gradient: bounded by the flipped rows' weight
+            l2mx = [G.grad_close(g, grads[i], f"grad {i}")
+                    for i, g in enumerate(g_gpu)]
+            _record("dqn_config2", path=path, flipped_rows=flipped, wgrad_rel_err_masked=worst,
+                    grad_l2_rel=max(x[0] for x in l2mx), grad_max_rel=max(x[1] for x in l2mx))
         t.optimizers()[0].fused_step(target=t.q_network_target.arena, tau=t.tau)
         assert abs(float(t._ws["loss"]) - lo) <= 2e-5 * max(1.0, abs(lo))
     # post-Adam parameters: an element whose gradient is within fp32 noise of zero moves by
-    # up to lr per step in either direction (Adam normalises the step), so bound every element
-    # by the total step size and require all but a vanishing fraction within 1e-5
+    # up to lr per step in either direction (Adam normalises the step), so every element is
+    # bounded by the total step size and the fraction off by more than 1e-5 is bounded at 10x
+    # the measured one
+    fracs = []
     for i, seq in enumerate(t.q_network.fc.dnn):
         d = (seq[0].weight.detach().cpu().double() - qo["W"][i].detach().double()).abs()
         assert float(d.max()) <= 2.0 * meta["n_updates"] * meta["lr"] * 1.01
-        assert float((d > 1e-5 * float(qo["W"][i].abs().max())).double().mean()) < 0.1
+        fracs.append(float((d > 1e-5 * float(qo["W"][i].abs().max())).double().mean()))
+    _record("dqn_config2_adam", path=path, outlier_frac=fracs)
+    assert max(fracs) < CONFIG2_MAX_ADAM_OUTLIER_FRAC, fracs
     for i, seq in enumerate(t.q_network_target.fc.dnn):
         assert G.rel_err(seq[0].weight, qt["W"][i]) < TOL
 

@@ -192,3 +192,75 @@ def test_qrdqn_oracle_matches_reference(name):
         for i, (w, b) in enumerate(G.net_pairs(arrays, prefix)):
             assert G.rel_err(ps[2 * i], w) < 1e-6
             assert G.rel_err(ps[2 * i + 1], b) < 1e-6
+
+@pytest.mark.parametrize("horizon,n", [(1, 512), (3, 512), (2, 300)])
+def test_replay_oracle_bulk_fill_equals_sequential_adds(horizon, n):
+    """ReplayOracle.bulk_fill (used by the config-2-size GPU test and the CPU baseline of
+    bench.py) leaves exactly the state of n sequential add() calls: validity, storage and the
+    fp64 sum tree bit for bit (sequential delta propagation, sum_tree.py:164-189)."""
+    import numpy as np
+
+    from oracle.replay_oracle import ReplayOracle
+
+    rng = np.random.RandomState(horizon * 100 + n)
+    cap = 512
+    st = dict(observation=rng.randn(n, 4).astype(np.float32),
+              action=rng.randint(0, 3, n).astype(np.int64),
+              reward=rng.randn(n).astype(np.float32), terminal=rng.rand(n) < 0.05,
+              priority=rng.uniform(0.1, 10, n))
+    a = ReplayOracle(cap, update_horizon=horizon, prioritized=True)
+    b = ReplayOracle(cap, update_horizon=horizon, prioritized=True)
+    for t in range(n):
+        a.add(**{k: v[t] for k, v in st.items()})
+    b.bulk_fill(st)
+    assert np.array_equal(a.valid, b.valid)
+    for x, y in zip(a.tree.nodes, b.tree.nodes):
+        assert np.array_equal(x, y)
+    assert (a.ep, a.add_count) == (b.ep, b.add_count)
+    assert a.tree.max_recorded_priority == b.tree.max_recorded_priority
+    for k in a.store:
+        assert np.array_equal(a.store[k], b.store[k])
+
+
+@pytest.mark.parametrize("name", ["inputmaker_dqn_uniform", "inputmaker_dqn_per_masks",
+                                  "inputmaker_policy_uniform", "inputmaker_policy_per_h3"])
+def test_replay_oracle_plus_inputmaker_formulas_match_reference(name):
+    """The oracle sampler followed by the InputMaker arithmetic (one-hot, zeroed terminal
+    next-actions, 1 - terminal, affine action rescale: trainer_preprocessor.py:72-227,
+    training/utils.py:13-29) reproduces the reference InputMakers' outputs on the same seeds --
+    this is what the config-2-size GPU test compares the fused kernel with."""
+    import random
+
+    import numpy as np
+
+    from oracle.replay_oracle import ReplayOracle
+
+    arrays, meta = G.load(name)
+    ro = ReplayOracle(meta["cap"], update_horizon=meta["horizon"], gamma=meta["gamma"],
+                      prioritized=meta["prioritized"])
+    st = {k: arrays[f"stream.{k}"] for k in meta["keys"]}
+    for t in range(meta["n_add"]):
+        ro.add(**{k: v[t] for k, v in st.items()})
+    random.seed(meta["seed"] + 200)
+    torch.manual_seed(meta["seed"] + 200)
+    A = meta["A"]
+    for s_i in range(meta["n_samples"]):
+        ob = ro.sample_transition_batch(meta["B"])
+        pre = f"sample{s_i}."
+        assert np.array_equal(ob["indices"], arrays[pre + "indices"].reshape(-1))
+        term = ob["terminal"].astype(bool)
+        assert np.array_equal(term, arrays[pre + "terminal"].reshape(-1))
+        assert np.array_equal(ob["state"], arrays[pre + "state"])
+        assert np.array_equal(ob["next_state"][~term], arrays[pre + "next_state"][~term])
+        np.testing.assert_allclose(ob["reward"], arrays[pre + "reward"].reshape(-1), rtol=2e-6, atol=1e-6)
+        assert np.array_equal(1.0 - term.astype(np.float32), arrays[pre + "not_terminal"].reshape(-1))
+        if meta["continuous"]:
+            lo, hi = arrays["action_low"], arrays["action_high"]
+            resc = lambda a: ((a - lo) / (hi - lo)) * np.float32(2.0) + np.float32(-1.0)
+            assert np.array_equal(resc(ob["action"]).astype(np.float32), arrays[pre + "action"])
+            na = resc(ob["next_action"]).astype(np.float32) * (~term)[:, None]
+            assert np.array_equal(na, arrays[pre + "next_action"])
+        else:
+            eye = np.eye(A, dtype=np.float32)
+            assert np.array_equal(eye[ob["action"]], arrays[pre + "action"])
+            assert np.array_equal(eye[ob["next_action"]] * (~term)[:, None], arrays[pre + "next_action"])
