@@ -39,7 +39,10 @@
 namespace rb200 {
 
 constexpr int kQR = 32;                                   // batch rows per CTA
-constexpr int kQStages = 3;                               // ring depth
+#ifndef RB200_QSTAGES
+#define RB200_QSTAGES 3
+#endif
+constexpr int kQStages = RB200_QSTAGES;                   // ring depth
 constexpr int kQStageBytes = 2 * (kQKC / 4) * kQFullLbo;  // hi + lo planes of one chunk
 // B operand (activations): per k quad 64 rows of 16 B -- rows 0-31 hold the hi parts of the 32
 // batch rows, rows 32-63 their lo parts -- plus 16 B of padding.  One N = 64 MMA against W_hi
@@ -74,6 +77,7 @@ struct QDev {
   int nsteps, last_fwd_step;
   int buf_off[3];  // operand buffers (bytes from the smem base); [2] holds dZ of the last layer
   int q_off, ldq, lin_off, bar_off;
+  int copy_split;   // bulk copies per weight chunk (>= 1): several smaller copies in flight
   int dbg_mode;     // profiling only: 1 skip the N=32 MMAs, 2 skip the N=64 MMAs, 3 skip both
   long long* dbg;  // optional timeline of block 0: [step][8] clock64 stamps (profiling builds)
   QStep steps[kQMaxSteps];
@@ -262,7 +266,12 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
           mbar_wait(done + stage, par);
           if (leader) {
             mbar_expect_tx(full + stage, bytes);
-            bulk_g2s(ring + stage * kQStageBytes, src, bytes, full + stage);
+            // several smaller bulk copies per chunk: the copy engine pipelines them, which
+            // shortens the time from "stage free" to "stage full" (the ring is latency-bound)
+            const uint32_t sub = ((bytes / (uint32_t)p.copy_split) + 15u) & ~15u;
+            unsigned char* dst = ring + stage * kQStageBytes;
+            for (uint32_t o = 0; o < bytes; o += sub)
+              bulk_g2s(dst + o, src + o, (bytes - o < sub) ? bytes - o : sub, full + stage);
           }
           src += bytes;
           if (++stage == kQStages) { stage = 0; par ^= 1u; }
@@ -812,6 +821,7 @@ extern "C" int rb200_dqn_td_step_tc(const rb200_mlp_t* q_net, const rb200_mlp_t*
   pl.dev.pack = static_cast<const unsigned char*>(pack_ws);
   pl.dev.dbg = g_tc_dbg;
   { const char* e = getenv("RB200_TC_DBG_MODE"); pl.dev.dbg_mode = e ? atoi(e) : 0; }
+  { const char* e = getenv("RB200_TC_COPY_SPLIT"); int v = e ? atoi(e) : 1; pl.dev.copy_split = v < 1 ? 1 : (v > 16 ? 16 : v); }
   cudaStream_t st = (cudaStream_t)stream;
   static size_t configured = 0;  // raised outside graph capture by the first (eager) call
   if (configured < pl.smem_bytes) {

@@ -42,7 +42,7 @@ class P2PExchange:
 
     MAX_BLOCKS = 148 * 4
 
-    def __init__(self, group=None, pool_bytes: int = 96 << 20):
+    def __init__(self, group=None, pool_bytes: int = 512 << 20):
         import ctypes as C
 
         import torch.distributed as dist
@@ -101,7 +101,7 @@ class P2PExchange:
 _EXCHANGES = {}
 
 
-def enable_p2p(group=None, pool_bytes: int = 96 << 20) -> P2PExchange:
+def enable_p2p(group=None, pool_bytes: int = 512 << 20) -> P2PExchange:
     """Create (once per process group) the peer-memory exchange; afterwards `dp_fused_step`
     uses the fused kernel instead of reduce + NCCL all-reduce + Adam."""
     key = id(group) if group is not None else 0

@@ -26,9 +26,20 @@ from ..replay_memory.prioritized_replay_buffer import PrioritizedReplayBuffer
 
 class FusedDqnStep:
     def __init__(self, trainer, replay_buffer, batch_size: int, process_group=None,
-                 slots: int = 2, prefetch: bool = False):
+                 slots: int = 2, prefetch: bool = False, shard=None):
+        """`shard = (rank, world)`: data-parallel strong scaling.  `batch_size`
+        is the GLOBAL minibatch; the replay buffer is replicated and every rank consumes the
+        identical host random stream, so all ranks select the same global indices, and this
+        rank gathers and trains on rows [rank*B/world, (rank+1)*B/world) only."""
         self.trainer = trainer
         self.rb = replay_buffer
+        self.B_global = batch_size
+        self.row0 = 0
+        if shard is not None and shard[1] > 1:
+            from .data_parallel import shard_rows
+
+            self.row0, hi = shard_rows(batch_size, shard[0], shard[1])
+            batch_size = hi - self.row0
         self.B = batch_size
         self.pg = process_group
         self.prioritized = isinstance(replay_buffer, PrioritizedReplayBuffer)
@@ -101,8 +112,30 @@ class FusedDqnStep:
         self._batches[1 - i] = nxt
         return loss
 
+    def _host_draw(self):
+        """This rank's rows of one GLOBAL host draw: (values, override positions, indices)."""
+        lo, hi = self.row0, self.row0 + self.B
+        if self.prioritized:
+            q, pos, idxs = self.rb.host_queries(self.B_global)
+            keep = [(p - lo, i) for p, i in zip(pos, idxs) if lo <= p < hi]
+            return q[lo:hi], [p for p, _ in keep], [i for _, i in keep]
+        n_valid = self.rb._num_valid_indices
+        if n_valid == 0:
+            raise RuntimeError(f"Cannot sample {self.B_global} since there are no valid indices so far.")
+        return torch.randint(n_valid, (self.B_global,))[lo:hi].numpy(), [], []
+
     def _sample(self, rnd_dev):
-        if rnd_dev is None:
+        if rnd_dev is None and self.B != self.B_global:
+            q, pos, idxs = self._host_draw()
+            qd = torch.from_numpy(np.ascontiguousarray(q)).to(self.dev)
+            if self.prioritized:
+                kw = {"query_dev": qd}
+                if pos:
+                    kw["overrides"] = (pos, idxs)
+            else:
+                kw = {"ranks_dev": qd}
+            batch = self.rb.sample_discrete_dqn_batch(self.B, self.A, **kw)
+        elif rnd_dev is None:
             batch = self.rb.sample_discrete_dqn_batch(self.B, self.A)
         elif self.prioritized:
             batch = self.rb.sample_discrete_dqn_batch(self.B, self.A, query_dev=rnd_dev)
@@ -139,7 +172,7 @@ class FusedDqnStep:
         else:
             self.rb._ensure_valid_index()
         if self.prioritized:
-            q, pos, idxs = self.rb.host_queries(self.B)
+            q, pos, idxs = self._host_draw()
             if pos:  # rare retry path: resolved on the host, run this update un-captured
                 qd = torch.from_numpy(q).to(self.dev)
                 if self.prefetch:
@@ -154,10 +187,7 @@ class FusedDqnStep:
                 return s["loss_host"]
             s["host"].numpy()[:] = q
         else:
-            n_valid = self.rb._num_valid_indices
-            if n_valid == 0:
-                raise RuntimeError(f"Cannot sample {self.B} since there are no valid indices so far.")
-            torch.randint(n_valid, (self.B,), out=s["host"])
+            s["host"].copy_(torch.from_numpy(self._host_draw()[0]))
         s["graph"].replay()
         s["done"].record()
         s["used"] = True

@@ -138,11 +138,15 @@ def _record(name, **kv):
             f.write(json.dumps({"test": name, **kv}) + "\n")
 
 
-# Bounds of test_dqn_config2_matches_oracle, each 10x what was measured on B200 (round 2,
-# gpurun_out/test_measurements.jsonl): rows whose ReLU pattern differs from the oracle's (a
-# hidden unit within ~5e-6 of 0 flips), and post-Adam elements off by more than 1e-5.
-CONFIG2_MAX_FLIPPED_ROWS = 60
-CONFIG2_MAX_ADAM_OUTLIER_FRAC = 0.02
+# Bounds of test_dqn_config2_matches_oracle, 10x what was measured on B200 (round 2, tcgen05
+# path: 0 rows whose ReLU pattern differs from the oracle's -- a hidden unit within ~5e-6 of 0
+# would flip -- weight gradients within 2.8e-6, post-Adam elements off by more than 1e-5:
+# 1.2e-4 of the first layer, none elsewhere).
+CONFIG2_MAX_FLIPPED_ROWS = 8
+CONFIG2_MAX_ADAM_OUTLIER_FRAC = 1.2e-3
+# the mma.sync row-tile kernel (the library's second K2, taken when shapes do not fit tcgen05)
+# accumulates its 3xTF32 products in a different order: per-row dZ measured 1.1e-5 at this size
+CONFIG2_DZ_TOL = {"tcgen05": TOL, "rows": 2e-5}
 
 
 @pytest.mark.parametrize("path", K2_PATHS)
@@ -219,7 +223,7 @@ def test_dqn_config2_matches_oracle(path, monkeypatch):
             for l in range(2):  # saved activations: 1e-5 everywhere (a flip moves h by < 1e-5)
                 assert G.rel_err(h_gpu[l], h_ref[l]) < TOL, ("hidden", l)
             for l in range(3):  # dLoss/dz per row: 1e-5 on the rows with the oracle's pattern
-                assert G.rel_err(dz_gpu[l][same], dz_ref[l][same]) < TOL, ("dz", l)
+                assert G.rel_err(dz_gpu[l][same], dz_ref[l][same]) < CONFIG2_DZ_TOL[path], ("dz", l)
             # weight gradients at 1e-5: the oracle's, with the flipped rows' contributions
             # replaced by what follows from the GPU's own dz on those rows
             inputs = [b["state"]] + h_ref[:2]
@@ -232,9 +236,9 @@ def test_dqn_config2_matches_oracle(path, monkeypatch):
                 gb_ = dzm.double().sum(0)
                 ew, eb = G.rel_err(g_gpu[2 * l], gw), G.rel_err(g_gpu[2 * l + 1], gb_)
                 worst = max(worst, ew, eb)
-                assert ew < TOL and eb < TOL, ("wgrad", l, ew, eb)
+                assert ew < CONFIG2_DZ_TOL[path] and eb < CONFIG2_DZ_TOL[path], ("wgrad", l, ew, eb)
             # and against the unmodified oracle gradient: bounded by the flipped rows' weight
-            l2mx = [G.grad_close(g, grads[i], f"grad {i}")
+            l2mx = [G.grad_close(g, grads[i], f"grad {i}", l2_tol=1e-4, max_tol=1e-4)
                     for i, g in enumerate(g_gpu)]
             _record("dqn_config2", path=path, flipped_rows=flipped, wgrad_rel_err_masked=worst,
                     grad_l2_rel=max(x[0] for x in l2mx), grad_max_rel=max(x[1] for x in l2mx))
