@@ -256,12 +256,40 @@ def check(rc, what=""):
         raise Rb200Error(f"{what} failed (rc={rc}): {msg}")
 
 
-def ptr(t):
-    """Device pointer of a torch tensor (None -> NULL)."""
-    return None if t is None else t.data_ptr()
+def ptr(t, device=None):
+    """Device pointer of a torch tensor (None -> NULL).  A host tensor -- or one on another
+    GPU than `device` -- would reach the kernel as a wild pointer (illegal address, sticky
+    context error), so it is refused here with a Python exception instead."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise Rb200Error("reagent_b200: a CPU tensor reached a CUDA entry point (call "
+                         "trainer.cuda() / batch.cuda() first; there is no CPU path)")
+    if device is not None and t.device != device:
+        raise Rb200Error(f"reagent_b200: tensor on {t.device}, expected {device}")
+    return t.data_ptr()
+
+
+def on_device(t, device):
+    """`t` on `device` (moved once if it was created elsewhere, e.g. trainer-owned constants
+    of a trainer that was built from already-CUDA networks and never .cuda()'d)."""
+    if t is None or (t.is_cuda and t.device == device):
+        return t
+    return t.to(device)
 
 
 def cur_stream():
     import torch
 
     return torch.cuda.current_stream().cuda_stream
+
+
+def require_current_device(device):
+    """Launches go to the CURRENT device's stream; tensors elsewhere would be wild pointers
+    there.  Multi-GPU callers run one process per GPU or wrap calls in torch.cuda.device()."""
+    import torch
+
+    if device.type != "cuda" or torch.cuda.current_device() != (device.index or 0):
+        raise Rb200Error(f"reagent_b200: tensors live on {device} but the current CUDA device is "
+                         f"cuda:{torch.cuda.current_device()} -- wrap the call in "
+                         f"torch.cuda.device({device.index})")

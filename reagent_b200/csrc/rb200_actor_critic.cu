@@ -383,12 +383,10 @@ ac_actor_rows_kernel(const Mlp actor, const Mlp q1, const Mlp q2, const AcDev p)
 #define RB200_LAUNCH_ACC(NT_, TM_, KC_, grid, smem, stream, ...)                              \
   do {                                                                                        \
     auto kfn = ac_critic_rows_kernel<NT_, TM_, KC_>;                                          \
-    static size_t configured_ = 0;                                                            \
-    if (configured_ < (size_t)(smem)) {                                                       \
-      cudaError_t e_ = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                            (int)(smem));                                     \
-      if (e_ != cudaSuccess) return check_cuda(e_, "cudaFuncSetAttribute(ac_critic)");        \
-      configured_ = (size_t)(smem);                                                           \
+    static SmemOptIn optin_ = {};                                                             \
+    {                                                                                         \
+      cudaError_t e_ = ensure_dynamic_smem(kfn, optin_, (size_t)(smem));                      \
+      if (e_ != cudaSuccess) return check_cuda(e_, "cudaFuncSetAttribute(ac_critic)");                                       \
     }                                                                                         \
     kfn<<<grid, NT_, smem, stream>>>(__VA_ARGS__);                                            \
   } while (0)
@@ -396,12 +394,10 @@ ac_actor_rows_kernel(const Mlp actor, const Mlp q1, const Mlp q2, const AcDev p)
 #define RB200_LAUNCH_ACA(NT_, TM_, KC_, grid, smem, stream, ...)                              \
   do {                                                                                        \
     auto kfn = ac_actor_rows_kernel<NT_, TM_, KC_>;                                           \
-    static size_t configured_ = 0;                                                            \
-    if (configured_ < (size_t)(smem)) {                                                       \
-      cudaError_t e_ = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                            (int)(smem));                                     \
-      if (e_ != cudaSuccess) return check_cuda(e_, "cudaFuncSetAttribute(ac_actor)");         \
-      configured_ = (size_t)(smem);                                                           \
+    static SmemOptIn optin_ = {};                                                             \
+    {                                                                                         \
+      cudaError_t e_ = ensure_dynamic_smem(kfn, optin_, (size_t)(smem));                      \
+      if (e_ != cudaSuccess) return check_cuda(e_, "cudaFuncSetAttribute(ac_actor)");                                       \
     }                                                                                         \
     kfn<<<grid, NT_, smem, stream>>>(__VA_ARGS__);                                            \
   } while (0)

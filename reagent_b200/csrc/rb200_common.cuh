@@ -93,6 +93,24 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Dynamic shared-memory opt-in of a kernel, remembered PER DEVICE (the attribute is per device
+// and per function): a high-water mark indexed by the current device id, so the first launch on
+// a second GPU of the same process opts in as well.  Racing threads at worst set the attribute
+// twice.  Raised outside CUDA-graph capture by the first eager call.
+struct SmemOptIn {
+  size_t configured[64];
+};
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, SmemOptIn& st, size_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && st.configured[dev] >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) st.configured[dev] = bytes;
+  return e;
+}
+
 // Error plumbing shared by the C-ABI translation units.
 void set_last_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);

@@ -9,12 +9,18 @@
 // (N = 32).  4096 rows therefore spread over 128 SMs instead of the 32 an M = 128-row tile
 // would use, and the accumulator of a layer is only 32 TMEM columns per 128 features.
 //
-//   weights      pre-split once per update into hi/lo TF32 planes and pre-tiled by
-//                dqn_tc_pack_kernel into the exact shared-memory image of each
-//                (128-feature tile, 16-k chunk) -- canonical K-major no-swizzle UMMA layout
-//                [k/4][row][4 floats], quad stride padded by 16 B.  The TD kernel streams those
-//                images through a 6-stage ring with 1-D bulk copies (cp.async.bulk ->
-//                mbarrier complete_tx), issued by the same elected thread that issues the MMAs.
+//   weights      pre-tiled once per update (by the Adam kernel, or dqn_tc_pack_kernel) into one
+//                fp32 image per (128-feature tile, 32-k chunk) -- [k/4][row][4 floats].  The TD
+//                kernel streams the images through a shared-memory ring with 1-D bulk copies
+//                (cp.async.bulk -> mbarrier complete_tx, producer warp); FOUR LOADER WARPS (one
+//                per TMEM lane quadrant; a thread owns one weight row) read "my row" with
+//                conflict-free 16-byte loads, split it into TF32 hi / lo in registers and store
+//                both into a ring of TENSOR MEMORY columns (tcgen05.st): the weights are the
+//                A operand of the MMAs FROM TENSOR MEMORY.  Every weight byte therefore crosses
+//                shared memory once in and once out as raw fp32 (8 B per parameter) instead of
+//                hi+lo in and hi+lo out through the MMA (16 B): the shared-memory data pipe,
+//                which bounded the previous version (77 KB per chunk at 128 B/clk), carries
+//                45 KB per chunk, and the MMAs read only the small B operand from it.
 //   activations  live in shared memory as hi/lo planes in the same canonical layout (rows =
 //                batch rows); the epilogue of layer l (tcgen05.ld -> bias -> activation -> split)
 //                writes them straight into the B operand of layer l+1 and, for the online
@@ -24,9 +30,12 @@
 //
 // Every thread of warps 0-7 owns one output feature (TMEM lane) in the epilogues, which makes
 // the bias a per-thread scalar and the operand stores bank-conflict free; warp 8 streams the
-// weights and warp 9 issues the MMAs (warp-uniform loops, one elected lane issues).  Synchronisation is mbarrier-only inside the step loop:
-//     full[s]  bulk copy landed        done[s]  MMAs of the chunk retired (tcgen05.commit)
-//     dready   a layer's accumulator is complete       opready  next B operand is in smem
+// weights, warp 9 issues the MMAs (warp-uniform loops, one elected lane issues), warps 10-13
+// move the weights from shared to tensor memory.  Synchronisation is mbarrier-only inside the
+// step loop:
+//     full[s]   bulk copy landed in smem stage s     sfree[s]  the loaders have read stage s
+//     afull[t]  TMEM stage t holds a split chunk     adone[t]  its MMAs retired (tcgen05.commit)
+//     dready    a layer's accumulator is complete    opready   next B operand is in smem
 //
 // Reference semantics: reagent/training/dqn_trainer.py:157-239, dqn_trainer_base.py:33-77,
 // 216-241 (see rb200_dqn.cu for the line-by-line map; the loss code is the same).
@@ -40,10 +49,12 @@ namespace rb200 {
 
 constexpr int kQR = 32;                                   // batch rows per CTA
 #ifndef RB200_QSTAGES
-#define RB200_QSTAGES 3
+#define RB200_QSTAGES 6
 #endif
-constexpr int kQStages = RB200_QSTAGES;                   // ring depth
-constexpr int kQStageBytes = 2 * (kQKC / 4) * kQFullLbo;  // hi + lo planes of one chunk
+constexpr int kQStages = RB200_QSTAGES;                   // shared-memory ring depth (raw fp32 chunks)
+constexpr int kQStageBytes = (kQKC / 4) * kQFullLbo;      // one chunk image
+constexpr int kAStages = 4;                               // tensor-memory ring depth (split chunks)
+constexpr int kAStageCols = 2 * kQKC;                     // hi columns then lo columns of a chunk
 // B operand (activations): per k quad 64 rows of 16 B -- rows 0-31 hold the hi parts of the 32
 // batch rows, rows 32-63 their lo parts -- plus 16 B of padding.  One N = 64 MMA against W_hi
 // then yields W_hi.X_hi in accumulator columns 0-31 and W_hi.X_lo in columns 32-63; a second
@@ -52,9 +63,13 @@ constexpr int kQStageBytes = 2 * (kQKC / 4) * kQFullLbo;  // hi + lo planes of o
 constexpr int kQLboB = 64 * 16 + 16;
 constexpr int kQLoOff = 32 * 4;                           // floats from a hi element to its lo
 constexpr int kQEpiThreads = 256;
-constexpr int kQThreads = kQEpiThreads + 64;              // + producer warp + MMA warp
-constexpr int kQTmemCols = 256;                           // 4 feature tiles x 64 columns
-constexpr int kQMaxTiles = kQTmemCols / 64;
+constexpr int kQLoaderWarps = 4;                          // one per TMEM lane quadrant
+constexpr int kQThreads = kQEpiThreads + 64 + 32 * kQLoaderWarps;  // + producer + MMA + loaders
+constexpr int kQMaxTiles = 4;                             // accumulators: 4 feature tiles x 64 columns
+constexpr int kQAccCols = kQMaxTiles * 64;
+constexpr int kQTmemCols = 512;                           // accumulators + the weight ring
+static_assert(kQAccCols + kAStages * kAStageCols <= kQTmemCols, "tensor memory budget");
+static_assert(kQKC == 32 || kQKC == 16, "loader warps move 16- or 32-k chunks");
 constexpr int kQMaxSteps = 4 * kMaxLayers;
 constexpr int kQMaxSmem = 232448;
 #ifndef RB200_TC_TIMELINE
@@ -77,14 +92,13 @@ struct QDev {
   int nsteps, last_fwd_step;
   int buf_off[3];  // operand buffers (bytes from the smem base); [2] holds dZ of the last layer
   int q_off, ldq, lin_off, bar_off;
-  int copy_split;   // bulk copies per weight chunk (>= 1): several smaller copies in flight
   int dbg_mode;     // profiling only: 1 skip the N=32 MMAs, 2 skip the N=64 MMAs, 3 skip both
   long long* dbg;  // optional timeline of block 0: [step][8] clock64 stamps (profiling builds)
   QStep steps[kQMaxSteps];
 };
 
 // ---------------------------------------------------------------------------
-// weight packing: fp32 arena -> hi/lo UMMA images
+// weight packing: fp32 arena -> tiled chunk images
 // ---------------------------------------------------------------------------
 struct PackJob {
   const float* W;   // nn.Linear weight [rows_src x ld]
@@ -112,8 +126,7 @@ __global__ void __launch_bounds__(256) dqn_tc_pack_kernel(const PackDev p) {
   const int t = local / kch, c = local - t * kch;
   const ChunkGeo g = chunk_geo(job.N, job.K, t, c);
   const int rows8 = (int)(g.lbo - 16) / 16, kl8 = g.ksteps * 8;
-  float* hi = reinterpret_cast<float*>(p.pack + job.pack_off + g.off);
-  float* lo = hi + (kl8 / 4) * (g.lbo / 4);
+  float* img = reinterpret_cast<float*>(p.pack + job.pack_off + g.off);
   const int m0 = 128 * t, k0 = kQKC * c;
   const int total = rows8 * kl8;
   constexpr int U = 4;
@@ -136,13 +149,8 @@ __global__ void __launch_bounds__(256) dqn_tc_pack_kernel(const PackDev p) {
       }
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (o[u] < 0) continue;
-      float h, l;
-      tf32_split(v[u], h, l);
-      hi[o[u]] = h;
-      lo[o[u]] = l;
-    }
+    for (int u = 0; u < U; ++u)
+      if (o[u] >= 0) img[o[u]] = v[u];
   }
 }
 
@@ -185,10 +193,45 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t t0, uint32_t t1, uint32_t (
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-// 160 registers x 320 threads and ~214 KB of shared memory leave room on the SM for one CTA
+// 32 consecutive TMEM columns of this thread's lane <- 32 registers
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n" ::"r"(taddr),
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+      "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]),
+      "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]),
+      "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+      "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+}
+// D[tmem] (+)= A[tmem: 128 lanes x 8 tf32 columns] . B[smem descriptor]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 144 registers x 448 threads and ~214 KB of shared memory leave room on the SM for one CTA
 // of the replay-sample kernel (48 registers x 256 threads, < 10 KB), so the sampler of the next
 // update can run on a second stream underneath this kernel instead of delaying its CTAs.
-__global__ void __maxnreg__(160)
+__global__ void __maxnreg__(144)
 dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -218,14 +261,17 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
   float* mask_s = act_s + kQR * A;                                // [kQR][A] next-action mask
   float* scal_s = mask_s + kQR * A;                               // [kQR][4] reward, not_terminal, discount src
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + p.bar_off);
-  uint64_t* done = full + kQStages;
-  uint64_t* dready = done + kQStages;  // one per accumulator tile (see the epilogue)
+  uint64_t* sfree = full + kQStages;
+  uint64_t* afull = sfree + kQStages;
+  uint64_t* adone = afull + kAStages;
+  uint64_t* dready = adone + kAStages;  // one per accumulator tile (see the epilogue)
   uint64_t* opready = dready + kQMaxTiles;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(opready + 1);
   const int ldq = p.ldq;
 
   if (tid == 0) {
-    for (int s = 0; s < kQStages; ++s) { mbar_init(full + s, 1); mbar_init(done + s, 1); }
+    for (int s = 0; s < kQStages; ++s) { mbar_init(full + s, 1); mbar_init(sfree + s, kQLoaderWarps); }
+    for (int t = 0; t < kAStages; ++t) { mbar_init(afull + t, kQLoaderWarps); mbar_init(adone + t, 1); }
     for (int t = 0; t < kQMaxTiles; ++t) mbar_init(dready + t, 1);
     mbar_init(opready, kQEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -245,33 +291,28 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
   const int role = __shfl_sync(0xffffffffu, warp, 0);
   if (role == kQEpiThreads / 32) {
     // =====================  weight producer warp (bulk copies)  =====================
-    // Free-running over the static chunk list; the `done` barriers of the ring are the only
-    // back-pressure, so up to kQStages chunks are in flight ahead of the tensor core.
+    // Free-running over the static chunk list; the `sfree` barriers of the ring are the only
+    // back-pressure, so up to kQStages chunks are in flight ahead of the loader warps.
     const bool leader = elect_one();
     int stage = 0;
     uint32_t par = 1;  // parity of the PREVIOUS use of `stage` (first lap: passes immediately)
     for (int s = 0; s < p.nsteps; ++s) {
       const QStep st = p.steps[s];
       const int mt = ceil_div(st.N, 128), kch = ceil_div(st.K, kQKC);
-      const uint32_t tile_stride = 2u * (uint32_t)(round_up8(st.K) / 4) * kQFullLbo;
+      const uint32_t tile_stride = (uint32_t)(round_up8(st.K) / 4) * kQFullLbo;
       for (int t = 0; t < mt; ++t) {
         const int rows = st.N - 128 * t;
         const uint32_t lbo = (uint32_t)(round_up8(rows < 128 ? rows : 128) * 16 + 16);
-        const uint32_t full_bytes = 2u * (kQKC / 4) * lbo;
+        const uint32_t full_bytes = (kQKC / 4) * lbo;
         const int klast = st.K - kQKC * (kch - 1);
-        const uint32_t last_bytes = 2u * (uint32_t)(round_up8(klast) / 4) * lbo;
+        const uint32_t last_bytes = (uint32_t)(round_up8(klast) / 4) * lbo;
         const unsigned char* src = p.pack + st.pack_off + (size_t)t * tile_stride;
         for (int c = 0; c < kch; ++c) {
           const uint32_t bytes = (c == kch - 1) ? last_bytes : full_bytes;
-          mbar_wait(done + stage, par);
+          mbar_wait(sfree + stage, par);
           if (leader) {
             mbar_expect_tx(full + stage, bytes);
-            // several smaller bulk copies per chunk: the copy engine pipelines them, which
-            // shortens the time from "stage free" to "stage full" (the ring is latency-bound)
-            const uint32_t sub = ((bytes / (uint32_t)p.copy_split) + 15u) & ~15u;
-            unsigned char* dst = ring + stage * kQStageBytes;
-            for (uint32_t o = 0; o < bytes; o += sub)
-              bulk_g2s(dst + o, src + o, (bytes - o < sub) ? bytes - o : sub, full + stage);
+            bulk_g2s(ring + stage * kQStageBytes, src, bytes, full + stage);
           }
           src += bytes;
           if (++stage == kQStages) { stage = 0; par ^= 1u; }
@@ -280,60 +321,101 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
     }
   } else if (role == kQEpiThreads / 32 + 1) {
     // =====================  MMA issuer warp  =====================
+    // A operand: the split weights in tensor memory (128 lanes = features, 8 columns per
+    // k step; hi columns then lo columns of the chunk).  B operand: the activations in
+    // shared memory (descriptor).
     const bool leader = elect_one();
     const uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
     const uint64_t desc_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, version 1
-    int stage = 0;
-    uint32_t par = 0;
+    int ts = 0;
+    uint32_t tpar = 0;
     for (int s = 0; s < p.nsteps; ++s) {
       const QStep st = p.steps[s];
       const int mt = ceil_div(st.N, 128), kch = ceil_div(st.K, kQKC);
       mbar_wait(opready, (uint32_t)s & 1u);
       tc_fence_after();
-      long long wfull = 0, wissue = 0, wcommit = 0;
       if (kTimeline && p.dbg && blockIdx.x == 0 && leader) p.dbg[s * 8 + 0] = clock64();
       const uint32_t b0 = ((smem_u32(smem_raw + p.buf_off[st.in_buf]) >> 4) & 0x3fffu) |
                           ((uint32_t)(kQLboB >> 4) << 16);
       for (int t = 0; t < mt; ++t) {
         const uint32_t d = tmem + (uint32_t)(t * 64);
-        const int rows = st.N - 128 * t;
-        const uint32_t lbo = (uint32_t)(round_up8(rows < 128 ? rows : 128) * 16 + 16);
         uint32_t bdesc = b0;  // advances by two k quads per MMA k step
         for (int c = 0; c < kch; ++c) {
           const int kl = st.K - kQKC * c;
           const int ksteps = round_up8(kl < kQKC ? kl : kQKC) / 8;
-          const long long w0 = (kTimeline && p.dbg) ? clock64() : 0;
-          mbar_wait(full + stage, par);
-          if (kTimeline && p.dbg) wfull += clock64() - w0;
-          const long long w1 = (kTimeline && p.dbg) ? clock64() : 0;
+          mbar_wait(afull + ts, tpar);
+          tc_fence_after();
           if (leader) {
-            uint32_t a_hi = ((smem_u32(ring + stage * kQStageBytes) >> 4) & 0x3fffu) |
-                            ((lbo >> 4) << 16);
-            const uint32_t lo_delta = ((uint32_t)(2 * ksteps) * lbo) >> 4;
-            const uint32_t a_step = (2u * lbo) >> 4;
+            uint32_t a_hi = tmem + (uint32_t)(kQAccCols + ts * kAStageCols);
             uint32_t bd = bdesc;
             for (int ks = 0; ks < ksteps; ++ks) {
               if (!kTimeline || !(p.dbg_mode & 2))
-                umma_tf32(d, desc_hi | a_hi, desc_hi | bd, idesc64, (c > 0 || ks > 0) ? 1u : 0u);
+                umma_tf32_ts(d, a_hi, desc_hi | bd, idesc64, (c > 0 || ks > 0) ? 1u : 0u);
               if (!kTimeline || !(p.dbg_mode & 1))
-                umma_tf32(d, desc_hi | (a_hi + lo_delta), desc_hi | bd, idesc32, 1u);
-              a_hi += a_step;
+                umma_tf32_ts(d, a_hi + kQKC, desc_hi | bd, idesc32, 1u);
+              a_hi += 8;
               bd += (2u * kQLboB) >> 4;
             }
-            const long long w2 = (kTimeline && p.dbg) ? clock64() : 0;
-            umma_commit(done + stage);
-            if (kTimeline && p.dbg) { wissue += w2 - w1; wcommit += clock64() - w2; }
+            umma_commit(adone + ts);  // this TMEM stage may be refilled once the MMAs retired
           }
           bdesc += (uint32_t)(kQKC / 4) * (kQLboB >> 4);
-          if (++stage == kQStages) { stage = 0; par ^= 1u; }
+          if (++ts == kAStages) { ts = 0; tpar ^= 1u; }
         }
         // one accumulator tile complete: its epilogue runs while the next tile's MMAs issue
         if (leader) umma_commit(dready + t);
       }
-      if (leader) {
-        if (kTimeline && p.dbg && blockIdx.x == 0) { p.dbg[s * 8 + 1] = clock64(); p.dbg[s * 8 + 2] = wfull; p.dbg[s * 8 + 6] = wissue; p.dbg[s * 8 + 7] = wcommit; }
-      }
+      if (kTimeline && p.dbg && blockIdx.x == 0 && leader) p.dbg[s * 8 + 1] = clock64();
       __syncwarp();
+    }
+  } else if (role >= kQEpiThreads / 32 + 2) {
+    // =====================  loader warps: shared memory -> TF32 split -> tensor memory  ======
+    // warp (10 + j) may touch TMEM lanes [32*((10+j)%4), +32): the four loader warps cover the
+    // four lane quadrants; lane i of a warp owns weight row 32*quadrant + i of the tile.
+    const int quadrant = warp & 3;
+    const int r = quadrant * 32 + lane;
+    int ss = 0, ts = 0;
+    uint32_t spar = 0, tpar = 1;  // TMEM stages start free (parity of the previous use)
+    for (int s = 0; s < p.nsteps; ++s) {
+      const QStep st = p.steps[s];
+      const int mt = ceil_div(st.N, 128), kch = ceil_div(st.K, kQKC);
+      for (int t = 0; t < mt; ++t) {
+        const int rows = st.N - 128 * t;
+        const int rows8 = round_up8(rows < 128 ? rows : 128);
+        const uint32_t lbo = (uint32_t)(rows8 * 16 + 16);
+        for (int c = 0; c < kch; ++c) {
+          const int kl = st.K - kQKC * c;
+          const int nq = round_up8(kl < kQKC ? kl : kQKC) / 4;
+          mbar_wait(full + ss, spar);
+          float hi[32], lo[32];
+          const unsigned char* src = ring + ss * kQStageBytes + r * 16;
+#pragma unroll
+          for (int qd = 0; qd < kQKC / 4; ++qd) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (qd < nq && r < rows8) v = *reinterpret_cast<const float4*>(src + qd * lbo);
+            float4 h, l;
+            split4(v, h, l);
+            hi[4 * qd + 0] = h.x; hi[4 * qd + 1] = h.y; hi[4 * qd + 2] = h.z; hi[4 * qd + 3] = h.w;
+            lo[4 * qd + 0] = l.x; lo[4 * qd + 1] = l.y; lo[4 * qd + 2] = l.z; lo[4 * qd + 3] = l.w;
+          }
+#pragma unroll
+          for (int i = kQKC; i < 32; ++i) { hi[i] = 0.f; lo[i] = 0.f; }
+          // the values are in registers: the shared-memory stage can be refilled
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sfree + ss);
+          mbar_wait(adone + ts, tpar);  // the MMAs that read this TMEM stage have retired
+          tc_fence_after();
+          const uint32_t ta = tmem + ((uint32_t)(quadrant * 32) << 16) +
+                              (uint32_t)(kQAccCols + ts * kAStageCols);
+          if (kQKC == 32) { tmem_st32(ta, hi); tmem_st32(ta + kQKC, lo); }
+          else { tmem_st16(ta, hi); tmem_st16(ta + kQKC, lo); }
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(afull + ts);
+          if (++ss == kQStages) { ss = 0; spar ^= 1u; }
+          if (++ts == kAStages) { ts = 0; tpar ^= 1u; }
+        }
+      }
     }
   } else {
     // =====================  operand producers / epilogue warps  =====================
@@ -749,7 +831,7 @@ static QPlan make_plan(const rb200_mlp_t* qn, const rb200_mlp_t* qtn, int double
   o += ((size_t)2 * kQR * qn->dims[L] + 4 * kQR + 8) * sizeof(float);
   o = (o + 15) & ~(size_t)15;
   pl.dev.bar_off = (int)o;
-  o += (2 * kQStages + kQMaxTiles + 1) * sizeof(uint64_t) + 16;
+  o += (2 * kQStages + 2 * kAStages + kQMaxTiles + 1) * sizeof(uint64_t) + 16;
   pl.smem_bytes = (o + 15) & ~(size_t)15;
   pl.ok = pl.smem_bytes <= (size_t)kQMaxSmem;
   return pl;
@@ -821,13 +903,11 @@ extern "C" int rb200_dqn_td_step_tc(const rb200_mlp_t* q_net, const rb200_mlp_t*
   pl.dev.pack = static_cast<const unsigned char*>(pack_ws);
   pl.dev.dbg = g_tc_dbg;
   { const char* e = getenv("RB200_TC_DBG_MODE"); pl.dev.dbg_mode = e ? atoi(e) : 0; }
-  { const char* e = getenv("RB200_TC_COPY_SPLIT"); int v = e ? atoi(e) : 1; pl.dev.copy_split = v < 1 ? 1 : (v > 16 ? 16 : v); }
   cudaStream_t st = (cudaStream_t)stream;
-  static size_t configured = 0;  // raised outside graph capture by the first (eager) call
-  if (configured < pl.smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(dqn_td_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+  static SmemOptIn optin = {};  // per device; raised outside graph capture by the first eager call
+  {
+    cudaError_t e = ensure_dynamic_smem(dqn_td_tc_kernel, optin, pl.smem_bytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(dqn_td_tc)");
-    configured = pl.smem_bytes;
   }
   const Mlp q = make_mlp(q_net), qt = make_mlp(q_target);
   const int grid = ceil_div(args->batch, kQR);

@@ -1,12 +1,15 @@
-// reagent_b200 -- layout of the packed hi/lo weight images of the tcgen05 TD kernel
+// reagent_b200 -- layout of the packed weight images of the tcgen05 TD kernel
 // (rb200_dqn_tc.cu), shared with the Adam kernel, which can write the images of the updated
 // parameters itself (rb200_optim.cu) instead of a separate packing launch.
 //
 // Image of an operand A[N rows x K] (N = output features, K = contraction): for every
-// (128-row tile t, kQKC-wide k chunk c) one block = hi plane then lo plane, each plane in the
-// canonical K-major no-swizzle UMMA layout [k/4][row][4 floats] with the k-quad stride (LBO)
-// padded by 16 B.  Rows / k past the matrix are zero (the buffer is zero-initialised once and
-// those positions are never written).
+// (128-row tile t, kQKC-wide k chunk c) one block of fp32 values laid out [k/4][row][4 floats]
+// with the k-quad stride (LBO) padded by 16 B, so that (a) one 1-D bulk copy moves a whole
+// chunk and (b) the loader warps of the TD kernel read "my row, quad q" as a conflict-free
+// 16-byte shared-memory load.  The TF32 hi/lo split happens in the TD kernel on the way into
+// Tensor Memory (the A operand of the MMAs), so the image holds every parameter ONCE.
+// Rows / k past the matrix are zero (the buffer is zero-initialised once and those positions
+// are never written).
 #pragma once
 #include "rb200_common.cuh"
 
@@ -29,9 +32,9 @@ __host__ __device__ __forceinline__ ChunkGeo chunk_geo(int N, int K, int t, int 
   g.lbo = (uint32_t)(rows8 * 16 + 16);
   const int kl = K - kQKC * c;
   const int kl8 = round_up8(kl < kQKC ? kl : kQKC);
-  g.bytes = 2u * (uint32_t)(kl8 / 4) * g.lbo;
-  g.off = (uint32_t)t * (2u * (uint32_t)(round_up8(K) / 4) * kQFullLbo) +
-          (uint32_t)c * (2u * (kQKC / 4) * g.lbo);
+  g.bytes = (uint32_t)(kl8 / 4) * g.lbo;
+  g.off = (uint32_t)t * ((uint32_t)(round_up8(K) / 4) * kQFullLbo) +
+          (uint32_t)c * ((kQKC / 4) * g.lbo);
   g.ksteps = kl8 / 8;
   g.k0q = c * (kQKC / 4);
   return g;
@@ -41,19 +44,17 @@ inline uint32_t image_bytes(int N, int K) {
   for (int t = 0; t < ceil_div(N, 128); ++t) {
     const int rows = N - 128 * t;
     const int rows8 = round_up8(rows < 128 ? rows : 128);
-    tot += 2u * (uint32_t)(round_up8(K) / 4) * (uint32_t)(rows8 * 16 + 16);
+    tot += (uint32_t)(round_up8(K) / 4) * (uint32_t)(rows8 * 16 + 16);
   }
   return tot;
 }
 
-// float offsets of element (m, k) of an [N x K] operand inside its image: hi at `hi`, lo at `lo`
-__host__ __device__ __forceinline__ void image_elem(int N, int K, int m, int k, uint32_t& hi,
-                                                    uint32_t& lo) {
+// float offset of element (m, k) of an [N x K] operand inside its image
+__host__ __device__ __forceinline__ uint32_t image_elem(int N, int K, int m, int k) {
   const int t = m >> 7, c = k / kQKC;
   const ChunkGeo g = chunk_geo(N, K, t, c);
   const int r = m & 127, kk = k - c * kQKC;
-  hi = g.off / 4 + (uint32_t)((kk >> 2) * (int)(g.lbo / 4) + r * 4 + (kk & 3));
-  lo = hi + (uint32_t)(2 * g.ksteps) * (g.lbo / 4);
+  return g.off / 4 + (uint32_t)((kk >> 2) * (int)(g.lbo / 4) + r * 4 + (kk & 3));
 }
 
 // Where the images of one Q-network pair live in the pack buffer (byte offsets); the order is

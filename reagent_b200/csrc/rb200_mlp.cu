@@ -51,12 +51,10 @@ __global__ void __launch_bounds__(NT, 1) mlp_fwd_rows_kernel(const Mlp net, cons
 #define RB200_LAUNCH_FWD(NT_, TM_, KC_, grid, smem, stream, ...)                                   \
   do {                                                                                        \
     auto kfn = mlp_fwd_rows_kernel<NT_, TM_, KC_>;                                                 \
-    static size_t configured_ = 0; /* set once (not inside CUDA-graph capture) */            \
-    if (configured_ < (size_t)(smem)) {                                                       \
-      cudaError_t e_ = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                            (int)(smem));                                     \
-      if (e_ != cudaSuccess) return check_cuda(e_, "cudaFuncSetAttribute(mlp_fwd)");               \
-      configured_ = (size_t)(smem);                                                           \
+    static SmemOptIn optin_ = {};                                                             \
+    {                                                                                         \
+      cudaError_t e_ = ensure_dynamic_smem(kfn, optin_, (size_t)(smem));                      \
+      if (e_ != cudaSuccess) return check_cuda(e_, "cudaFuncSetAttribute(mlp_fwd)");                                       \
     }                                                                                         \
     kfn<<<grid, NT_, smem, stream>>>(__VA_ARGS__);                                       \
   } while (0)

@@ -203,7 +203,7 @@ struct AdamDev {
   TcPackView pv;
 };
 
-// hi/lo images of one updated weight (and of its updated target) for the tcgen05 TD kernel
+// images of one updated weight (and of its updated target) for the tcgen05 TD kernel
 __device__ __forceinline__ void adam_pack_weight(const TcPackView& pv, long long i, float p,
                                                  bool has_target, float tgt) {
   for (int l = 0; l < pv.n_layers; ++l) {
@@ -211,26 +211,11 @@ __device__ __forceinline__ void adam_pack_weight(const TcPackView& pv, long long
     const long long rel = i - pv.w_off[l];
     if (rel < 0 || rel >= (long long)N * K) continue;
     const int m = (int)(rel / K), k = (int)(rel - (long long)m * K);
-    uint32_t hi, lo;
-    float h, lw;
-    image_elem(N, K, m, k, hi, lo);
-    tf32_split(p, h, lw);
-    float* f = pv.pack + pv.on_fwd[l] / 4;
-    f[hi] = h;
-    f[lo] = lw;
-    if (has_target) {
-      float th, tl;
-      tf32_split(tgt, th, tl);
-      float* ft = pv.pack + pv.tg_fwd[l] / 4;
-      ft[hi] = th;
-      ft[lo] = tl;
-    }
-    if (pv.has_bwd && l >= 1) {  // transposed operand: rows = K_l features, contraction = N_l
-      image_elem(K, N, k, m, hi, lo);
-      float* fb = pv.pack + pv.on_bwd[l] / 4;
-      fb[hi] = h;
-      fb[lo] = lw;
-    }
+    const uint32_t pos = image_elem(N, K, m, k);
+    pv.pack[pv.on_fwd[l] / 4 + pos] = p;
+    if (has_target) pv.pack[pv.tg_fwd[l] / 4 + pos] = tgt;
+    // transposed operand of the backward: rows = K_l features, contraction = N_l
+    if (pv.has_bwd && l >= 1) pv.pack[pv.on_bwd[l] / 4 + image_elem(K, N, k, m)] = p;
     return;
   }
 }

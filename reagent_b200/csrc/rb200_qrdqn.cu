@@ -231,12 +231,10 @@ __global__ void __launch_bounds__(256) qr_head_kernel(const QrDev d) {
   template <int NT_, int TM_, int KC_, typename... Args>                                        \
   static int launch_##TAG(dim3 grid, size_t smem, cudaStream_t st, Args... args) {              \
     auto kfn = KERN<NT_, TM_, KC_>;                                                             \
-    static size_t configured_ = 0;                                                              \
-    if (configured_ < smem) {                                                                   \
-      cudaError_t e_ = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                            (int)smem);                                         \
+    static SmemOptIn optin_ = {};                                                               \
+    {                                                                                           \
+      cudaError_t e_ = ensure_dynamic_smem(kfn, optin_, smem);                                  \
       if (e_ != cudaSuccess) return check_cuda(e_, "cudaFuncSetAttribute(" #TAG ")");           \
-      configured_ = smem;                                                                       \
     }                                                                                           \
     kfn<<<grid, NT_, smem, st>>>(args...);                                                      \
     return RB200_OK;                                                                            \

@@ -220,11 +220,10 @@ extern "C" int rb200_linear_forward_tc(const float* W, const float* b, int32_t a
                                        int32_t N, const float* in, int32_t batch, float* out,
                                        void* stream) {
   if (!W || !in || !out || K <= 0 || N <= 0 || batch <= 0) { set_last_error("rb200_linear_forward_tc: bad argument"); return RB200_E_INVALID; }
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_linear_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+  static SmemOptIn optin = {};
+  {
+    cudaError_t e = ensure_dynamic_smem(tc_linear_fwd_kernel, optin, (size_t)kTcSmemBytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tc_linear_fwd)");
-    configured = true;
   }
   TcDev p{in, W, b, out, batch, K, N, act};
   dim3 grid(ceil_div(batch, kTcM), ceil_div(N, kTcN));

@@ -65,12 +65,13 @@ class ActorCriticBase(RLTrainerMixin, ReAgentLightningModule):
         if not state.is_cuda:
             raise _lib.Rb200Error(
                 f"{type(self).__name__}: training batch must be on the GPU (no CPU path)")
+        _lib.require_current_device(state.device)
         a = _lib.AcArgsT()
 
         def P(t):
-            t = _f32c(t)
+            t = _lib.on_device(_f32c(t), state.device)
             keep.append(t)
-            return _lib.ptr(t)
+            return _lib.ptr(t, state.device)
 
         a.batch = state.shape[0]
         a.algo = self.ALGO

@@ -177,15 +177,16 @@ class DQNTrainer(DQNTrainerBaseLightning):
         if not state.is_cuda:
             raise _lib.Rb200Error(
                 "DQNTrainer: training batch must be on the GPU (reagent_b200 has no CPU path)")
+        _lib.require_current_device(state.device)
         B = state.shape[0]
         ws = self._workspace(B, state.device)
         a = _lib.DqnArgsT()
         keep = []
 
         def P(t):
-            t = _f32c(t)
+            t = _lib.on_device(_f32c(t), state.device)
             keep.append(t)
-            return _lib.ptr(t)
+            return _lib.ptr(t, state.device)
 
         a.batch = B
         a.state = P(state)

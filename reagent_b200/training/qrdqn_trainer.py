@@ -118,6 +118,7 @@ class QRDQNTrainer(DQNTrainerBaseLightning):
         state = _f32c(batch.state.float_features)
         if not state.is_cuda:
             raise _lib.Rb200Error("QRDQNTrainer: training batch must be on the GPU (no CPU path)")
+        _lib.require_current_device(state.device)
         next_state = _f32c(batch.next_state.float_features)
         B = state.shape[0]
         ws = self._workspace(B, state.device)
@@ -133,9 +134,9 @@ class QRDQNTrainer(DQNTrainerBaseLightning):
         keep = []
 
         def P(t):
-            t = _f32c(t)
+            t = _lib.on_device(_f32c(t), state.device)
             keep.append(t)
-            return _lib.ptr(t)
+            return _lib.ptr(t, state.device)
 
         a = _lib.QrdqnArgsT()
         a.batch, a.num_actions, a.num_atoms = B, self.num_actions, self.num_atoms

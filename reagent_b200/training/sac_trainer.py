@@ -78,12 +78,22 @@ class SACTrainer(ActorCriticBase):
                 torch.tensor([np.log(self.entropy_temperature)], dtype=torch.float32))
         else:
             self.target_entropy = target_entropy
-        self.register_buffer("_alpha_dev", torch.tensor([float(entropy_temperature)]))
+        # not part of the state_dict (the reference has no such key): re-derived from log_alpha
+        self.register_buffer("_alpha_dev", torch.tensor([float(entropy_temperature)]),
+                             persistent=False)
+        self.register_load_state_dict_post_hook(SACTrainer._rederive_alpha)
         self.logged_action_uniform_prior = logged_action_uniform_prior
         self.add_kld_to_loss = False
         self.crr_config = None
         self.backprop_through_log_prob = backprop_through_log_prob
         self.minibatch_size = minibatch_size
+
+    @staticmethod
+    def _rederive_alpha(module, incompatible_keys):
+        if module.alpha_optimizer is not None:  # sac_trainer.py:322
+            with torch.no_grad():
+                module._alpha_dev.copy_(module.log_alpha.data.exp().to(module._alpha_dev.device))
+            module.entropy_temperature = module._alpha_dev
 
     def configure_optimizers(self):
         """q1, q2, actor, alpha, SoftUpdate (sac_trainer.py:148-193)."""
@@ -109,7 +119,14 @@ class SACTrainer(ActorCriticBase):
 
     # ---- kernel argument fillers --------------------------------------------------
     def _fill_critic(self, a, keep):
-        a.alpha = self._alpha_dev.data_ptr()
+        dev = self._ws["dev"]
+        if self._alpha_dev.device != dev:  # trainer built from CUDA networks, never .cuda()'d
+            self._alpha_dev = self._alpha_dev.to(dev)
+            if self.alpha_optimizer is not None and self.log_alpha.device != dev:
+                raise _lib.Rb200Error("SACTrainer: log_alpha is not on the networks' device -- "
+                                      "move the trainer with .cuda()/.to(device) before "
+                                      "configure_optimizers()")
+        a.alpha = _lib.ptr(self._alpha_dev, dev)
         a.target_entropy = float(self.target_entropy)
         a.backprop_through_log_prob = int(bool(self.backprop_through_log_prob))
 
@@ -123,7 +140,7 @@ class SACTrainer(ActorCriticBase):
         a.noise_cur = nz.data_ptr()
         if self.alpha_optimizer is not None:
             a.alpha_grad = ws["alpha_grad"].data_ptr()
-            a.log_alpha = self.log_alpha.data.data_ptr()
+            a.log_alpha = _lib.ptr(self.log_alpha.data, ws["dev"])
 
     def _alpha_arena(self):
         arena = getattr(self.log_alpha, "_rb200_arena", None)

@@ -1,7 +1,7 @@
 // Host-only consistency check of the tcgen05 weight-image layout (rb200_dqn_tc_layout.cuh):
 // the element -> offset map used by the Adam kernel (image_elem) must be a bijection onto the
-// positions the pack kernel writes (chunk_geo + its in-chunk formula), hi and lo planes must
-// not collide, and everything must stay inside image_bytes().  Compiled with nvcc, run on the CPU.
+// positions the pack kernel writes (chunk_geo + its in-chunk formula), chunks must not collide,
+// and everything must stay inside image_bytes().  Compiled with nvcc, run on the CPU.
 #include <cstdio>
 #include <cstdlib>
 #include <set>
@@ -23,27 +23,24 @@ static int check(int N, int K) {
       for (int m = 0; m < rows8; ++m)
         for (int kk = 0; kk < kl8; ++kk) {
           const uint32_t hi = g.off / 4 + (kk >> 2) * (g.lbo / 4) + m * 4 + (kk & 3);
-          const uint32_t lo = hi + (kl8 / 4) * (g.lbo / 4);
-          if (hi >= total || lo >= total) { printf("oob N=%d K=%d\n", N, K); return 1; }
-          if (owner[hi] != -1 || owner[lo] != -1) { printf("collision N=%d K=%d\n", N, K); return 1; }
+          if (hi >= total) { printf("oob N=%d K=%d\n", N, K); return 1; }
+          if (owner[hi] != -1) { printf("collision N=%d K=%d\n", N, K); return 1; }
           const bool real = 128 * t + m < N && kQKC * c + kk < K;
           owner[hi] = real ? 1 : 0;
-          owner[lo] = real ? 2 : 0;
         }
     }
-  // the Adam-side map hits exactly the "real" positions, hi on hi and lo on lo
+  // the Adam-side map hits exactly the "real" positions
   long long real_hi = 0;
   for (uint32_t i = 0; i < total; ++i) real_hi += owner[i] == 1;
   if (real_hi != (long long)N * K) { printf("count N=%d K=%d\n", N, K); return 1; }
   for (int m = 0; m < N; ++m)
     for (int k = 0; k < K; ++k) {
-      uint32_t hi, lo;
-      image_elem(N, K, m, k, hi, lo);
-      if (hi >= total || lo >= total || owner[hi] != 1 || owner[lo] != 2) {
+      const uint32_t hi = image_elem(N, K, m, k);
+      if (hi >= total || owner[hi] != 1) {
         printf("image_elem mismatch N=%d K=%d m=%d k=%d\n", N, K, m, k);
         return 1;
       }
-      owner[hi] = owner[lo] = 3;  // each position exactly once
+      owner[hi] = 3;  // each position exactly once
     }
   return 0;
 }

@@ -1,11 +1,12 @@
 """Model check of the mbarrier protocol of the tcgen05 TD kernel (reagent_b200/csrc/rb200_dqn_tc.cu).
 
 The kernel's step loop is synchronised only by mbarriers that are waited on by PARITY:
-  full[s] / done[s]   weight ring (producer warp <-> MMA warp)
+  full[s] / sfree[s]  shared-memory weight ring (producer warp <-> 4 loader warps)
+  afull[t] / adone[t] tensor-memory weight ring (4 loader warps <-> MMA warp)
   dready[t]           accumulator tile t complete (MMA warp -> 8 epilogue warps), one per tile
   opready             next B operand in shared memory (epilogue threads -> MMA warp)
 A parity wait cannot tell "the phase I want" from "two phases later", so the protocol is only
-correct if no waiter can fall two completions behind.  This test restates the three roles as
+correct if no waiter can fall two completions behind.  This test restates the four roles as
 small state machines over an exact mbarrier model (completion counter; `wait(parity)` passes iff
 the counter's parity differs), runs them under many random interleavings and network shapes and
 asserts (a) progress to the end (no deadlock) and (b) that no waiter ever faces a barrier that
@@ -17,7 +18,9 @@ import random
 
 import pytest
 
-STAGES = 3  # kQStages
+STAGES = 6   # kQStages (shared memory)
+ASTAGES = 4  # kAStages (tensor memory)
+LOADERS = 4  # loader warps: one arrival each on sfree / afull
 
 
 class MBar:
@@ -50,7 +53,9 @@ def wait_ok(bar, intended):
 def simulate(steps, n_epi, rng, shared_dready=False, max_ticks=200000):
     """steps: list of (tiles, chunks_per_tile).  Returns True when every agent finished."""
     full = [MBar(1) for _ in range(STAGES)]
-    done = [MBar(1) for _ in range(STAGES)]
+    sfree = [MBar(LOADERS) for _ in range(STAGES)]
+    afull = [MBar(LOADERS) for _ in range(ASTAGES)]
+    adone = [MBar(1) for _ in range(ASTAGES)]
     ntile_bars = 1 if shared_dready else 4
     dready = [MBar(1) for _ in range(ntile_bars)]
     opready = MBar(n_epi)
@@ -62,24 +67,40 @@ def simulate(steps, n_epi, rng, shared_dready=False, max_ticks=200000):
         while n < total_chunks:
             stage, use = n % STAGES, n // STAGES
             if use > 0:
-                while not wait_ok(done[stage], use):
+                while not wait_ok(sfree[stage], use):
                     yield
             pending_events.append((tick[0] + rng.randint(1, 30), full[stage].arrive))
             n += 1
             yield
 
+    def loader():
+        for n in range(total_chunks):
+            ss, suse = n % STAGES, n // STAGES
+            ts, tuse = n % ASTAGES, n // ASTAGES
+            while not wait_ok(full[ss], suse + 1):
+                yield
+            for _ in range(rng.randint(0, 3)):  # shared-memory loads + split
+                yield
+            sfree[ss].arrive()
+            if tuse > 0:
+                while not wait_ok(adone[ts], tuse):
+                    yield
+            for _ in range(rng.randint(0, 3)):  # tcgen05.st + wait::st
+                yield
+            afull[ts].arrive()
+            yield
+
     def mma():
         n = 0
-        tile_uses = [0] * ntile_bars
         for s, (tiles, chunks) in enumerate(steps):
             while not wait_ok(opready, s + 1):
                 yield
             for t in range(tiles):
                 for _ in range(chunks):
-                    stage, use = n % STAGES, n // STAGES
-                    while not wait_ok(full[stage], use + 1):
+                    ts, tuse = n % ASTAGES, n // ASTAGES
+                    while not wait_ok(afull[ts], tuse + 1):
                         yield
-                    pending_events.append((tick[0] + rng.randint(1, 12), done[stage].arrive))
+                    pending_events.append((tick[0] + rng.randint(1, 12), adone[ts].arrive))
                     n += 1
                     yield
                 bar = dready[0 if shared_dready else t]
@@ -103,7 +124,8 @@ def simulate(steps, n_epi, rng, shared_dready=False, max_ticks=200000):
             yield
 
     tick = [0]
-    agents = [producer(), mma()] + [epilogue(rng.choice([3, 10, 40])) for _ in range(n_epi)]
+    agents = ([producer(), mma()] + [loader() for _ in range(LOADERS)]
+              + [epilogue(rng.choice([3, 10, 40])) for _ in range(n_epi)])
     alive = list(agents)
     while alive and tick[0] < max_ticks:
         tick[0] += 1
