@@ -228,10 +228,10 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
-// 144 registers x 448 threads and ~214 KB of shared memory leave room on the SM for one CTA
+// 128 registers x 448 threads (the register file is 16 K per SM sub-partition: 4 warps x 32 x 128) and ~214 KB of shared memory leave room on the SM for one CTA
 // of the replay-sample kernel (48 registers x 256 threads, < 10 KB), so the sampler of the next
 // update can run on a second stream underneath this kernel instead of delaying its CTAs.
-__global__ void __maxnreg__(144)
+__global__ void __maxnreg__(128)
 dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -334,6 +334,7 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
       const int mt = ceil_div(st.N, 128), kch = ceil_div(st.K, kQKC);
       mbar_wait(opready, (uint32_t)s & 1u);
       tc_fence_after();
+      long long wafull = 0;
       if (kTimeline && p.dbg && blockIdx.x == 0 && leader) p.dbg[s * 8 + 0] = clock64();
       const uint32_t b0 = ((smem_u32(smem_raw + p.buf_off[st.in_buf]) >> 4) & 0x3fffu) |
                           ((uint32_t)(kQLboB >> 4) << 16);
@@ -343,7 +344,9 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
         for (int c = 0; c < kch; ++c) {
           const int kl = st.K - kQKC * c;
           const int ksteps = round_up8(kl < kQKC ? kl : kQKC) / 8;
+          const long long w0 = (kTimeline && p.dbg) ? clock64() : 0;
           mbar_wait(afull + ts, tpar);
+          if (kTimeline && p.dbg) wafull += clock64() - w0;
           tc_fence_after();
           if (leader) {
             uint32_t a_hi = tmem + (uint32_t)(kQAccCols + ts * kAStageCols);
@@ -364,7 +367,7 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
         // one accumulator tile complete: its epilogue runs while the next tile's MMAs issue
         if (leader) umma_commit(dready + t);
       }
-      if (kTimeline && p.dbg && blockIdx.x == 0 && leader) p.dbg[s * 8 + 1] = clock64();
+      if (kTimeline && p.dbg && blockIdx.x == 0 && leader) { p.dbg[s * 8 + 1] = clock64(); p.dbg[s * 8 + 2] = wafull; }
       __syncwarp();
     }
   } else if (role >= kQEpiThreads / 32 + 2) {
@@ -378,6 +381,7 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
     for (int s = 0; s < p.nsteps; ++s) {
       const QStep st = p.steps[s];
       const int mt = ceil_div(st.N, 128), kch = ceil_div(st.K, kQKC);
+      long long lwfull = 0, lwdone = 0;
       for (int t = 0; t < mt; ++t) {
         const int rows = st.N - 128 * t;
         const int rows8 = round_up8(rows < 128 ? rows : 128);
@@ -385,7 +389,9 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
         for (int c = 0; c < kch; ++c) {
           const int kl = st.K - kQKC * c;
           const int nq = round_up8(kl < kQKC ? kl : kQKC) / 4;
+          const long long l0 = (kTimeline && p.dbg) ? clock64() : 0;
           mbar_wait(full + ss, spar);
+          if (kTimeline && p.dbg) lwfull += clock64() - l0;
           float hi[32], lo[32];
           const unsigned char* src = ring + ss * kQStageBytes + r * 16;
 #pragma unroll
@@ -402,7 +408,9 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
           // the values are in registers: the shared-memory stage can be refilled
           __syncwarp();
           if (lane == 0) mbar_arrive(sfree + ss);
+          const long long l1 = (kTimeline && p.dbg) ? clock64() : 0;
           mbar_wait(adone + ts, tpar);  // the MMAs that read this TMEM stage have retired
+          if (kTimeline && p.dbg) lwdone += clock64() - l1;
           tc_fence_after();
           const uint32_t ta = tmem + ((uint32_t)(quadrant * 32) << 16) +
                               (uint32_t)(kQAccCols + ts * kAStageCols);
@@ -415,6 +423,10 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
           if (++ss == kQStages) { ss = 0; spar ^= 1u; }
           if (++ts == kAStages) { ts = 0; tpar ^= 1u; }
         }
+      }
+      if (kTimeline && p.dbg && blockIdx.x == 0 && quadrant == 0 && lane == 0) {
+        p.dbg[s * 8 + 6] = lwfull;
+        p.dbg[s * 8 + 7] = lwdone;
       }
     }
   } else {
