@@ -386,6 +386,46 @@ def inputmaker_case(name, *, prioritized, continuous, cap, n_add, B, horizon=1, 
 
 
 # ---------------------------------------------------------------------------
+# normalization parameter inference (reagent/preprocessing/normalization.py:45-173,
+# identify_types.py:63-73)
+# ---------------------------------------------------------------------------
+def normalization_case(name, seed=0, n=2000):
+    from dataclasses import asdict
+    norm = ref("reagent.preprocessing.normalization")
+    ident = ref("reagent.preprocessing.identify_types")
+    rng = np.random.RandomState(seed)
+    samples = {
+        "binary": (rng.rand(n) < 0.3).astype(np.float32),
+        "constant": np.full(n, 2.5, dtype=np.float32),
+        "probability": rng.rand(n).astype(np.float32),
+        "enum": rng.randint(0, 7, n).astype(np.float32),
+        "normal": (3.0 + 2.0 * rng.randn(n)).astype(np.float32),
+        "lognormal": rng.lognormal(0.0, 1.0, n).astype(np.float32),
+        "bimodal": np.concatenate([rng.randn(n // 2) - 20, rng.randn(n - n // 2) * 0.1 + 30]).astype(np.float32),
+        "heavy_tail": rng.standard_cauchy(n).astype(np.float32),
+        "tiny_range": (5.0 + 1e-5 * rng.rand(n)).astype(np.float32),
+        "neg_ints": rng.randint(-3, 4, n).astype(np.float32),
+    }
+    forced = [("normal", ident.BOXCOX), ("normal", ident.QUANTILE), ("lognormal", ident.CONTINUOUS),
+              ("normal", ident.DO_NOT_PREPROCESS), ("normal", ident.CONTINUOUS_ACTION),
+              ("enum", ident.ENUM)]
+    arrays, expected = {}, {}
+    for k, v in samples.items():
+        arrays[f"values.{k}"] = v
+        expected[f"auto.{k}"] = {"type": ident.identify_type(v), "params": None}
+        p = norm.identify_parameter(k, v.copy())
+        expected[f"auto.{k}"]["params"] = None if p is None else asdict(p)
+    for k, ft in forced:
+        p = norm.identify_parameter(k, samples[k].copy(), feature_type=ft)
+        expected[f"forced.{k}.{ft}"] = None if p is None else asdict(p)
+    p = norm.identify_parameter("lognormal", samples["lognormal"].copy(), skip_box_cox=True)
+    expected["skip_box_cox.lognormal"] = asdict(p)
+    p = norm.identify_parameter("heavy_tail", samples["heavy_tail"].copy(), skip_quantiles=True)
+    expected["skip_quantiles.heavy_tail"] = asdict(p)
+    _save(name, arrays, dict(kind="normalization", expected=expected))
+
+
+# ---------------------------------------------------------------------------
 # dense preprocessor
 # ---------------------------------------------------------------------------
 def preprocessor_case(name, seed=0, B=64):
@@ -722,6 +762,7 @@ def main(only=None):
     add(inputmaker_case, "inputmaker_dqn_per_masks", prioritized=True, continuous=False, cap=256, n_add=200, B=48, seed=1, with_masks=True, horizon=3, gamma=0.95)
     add(inputmaker_case, "inputmaker_policy_uniform", prioritized=False, continuous=True, cap=128, n_add=250, B=32, A=3, seed=2)
     add(inputmaker_case, "inputmaker_policy_per_h3", prioritized=True, continuous=True, cap=256, n_add=400, B=40, A=5, seed=3, horizon=3, gamma=0.97)
+    add(normalization_case, "normalization_identify")
     add(preprocessor_case, "preprocessor_all_types")
     add(batch_preprocessor_case, "batch_preprocessor")
     add(sampler_case, "act_samplers")

@@ -3,8 +3,8 @@
 in-scope fields are kept; `.cuda()/.to()/.cpu()` fan out over tensor members like
 TensorDataClass.__getattr__ does."""
 import dataclasses
-from dataclasses import dataclass
-from typing import Optional
+from dataclasses import dataclass, field
+from typing import List, Optional
 
 import torch
 
@@ -129,3 +129,20 @@ class PolicyNetworkInput(BaseInput):
             next_action=FeatureData(batch["next_action"]),
             extras=batch.get("extras"),
         )
+
+
+# ---- dense feature configuration (core/types.py:152-155, :181-215); sparse id-list features
+# are out of scope of this package, so the config is dense-only ----
+@dataclass
+class FloatFeatureInfo:
+    name: str
+    feature_id: int
+
+
+@dataclass
+class ModelFeatureConfig:
+    float_feature_infos: List[FloatFeatureInfo] = field(default_factory=list)
+
+    @property
+    def only_dense(self):
+        return True
