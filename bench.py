@@ -580,6 +580,10 @@ def run_dqn(env, args, clocks):
     if world > 1:
         tw = build_trainer(cfg, dev)
         random.seed(4321 + env.rank)
+        # one eager update first: lazy allocations (workspaces, the optimizer's slice of the
+        # peer-memory pool) must not happen inside the graph capture
+        tw.train_batch(rb.sample_discrete_dqn_batch(Bg, cfg["A"]), process_group=pg)
+        torch.cuda.synchronize()
         qw, qt_ = draw(W, Bg, slice(0, Bg)), draw(K, Bg, slice(0, Bg))
         gw = capture_device_only(tw, rb, Bg, W, qw, pg)
         gt = capture_device_only(tw, rb, Bg, K, qt_, pg)

@@ -116,20 +116,23 @@ int rb200_mlp_forward(const rb200_mlp_t* net, const float* in0, int32_t d0, cons
 
 /* ------------------------------------------------------------------------- */
 /* Dueling head folded into a Linear (rb200_dueling.cu).  Replaces the head arithmetic of     */
-/* DuelingQNetwork._get_values (reagent/models/dueling_q_network.py:92-103):                   */
-/*   q = value + advantage - mean_a(advantage)                                                 */
-/* `fold` builds the equivalent last layer W_q [A, 2H] / b_q [A] from the true parameters      */
-/* (advantage head W_adv [A,H], b_adv [A]; value head w_val [1,H], b_val [1]) so that every    */
-/* MLP kernel of this library runs a dueling network as a plain MLP; `unfold` maps the gradient */
-/* of that layer back onto the true parameters in each of `splits` gradient slabs (offsets in   */
-/* floats from the slab start) and zeroes the folded layer's gradient.                          */
+/* DuelingQNetwork._get_values (reagent/models/dueling_q_network.py:92-103), with atoms:       */
+/*   q[a,n] = value[n] + advantage[a,n] - mean_{a',n'}(advantage)     (num_atoms = 1: DQN)     */
+/* `fold` builds the equivalent last layer W_q [A*N, 2H] / b_q [A*N] (row a*N+n) from the true  */
+/* parameters (advantage head W_adv [A*N,H], b_adv [A*N]; value head w_val [N,H], b_val [N]) so */
+/* that every MLP kernel of this library runs a dueling network as a plain MLP; `unfold` maps   */
+/* the gradient of that layer back onto the true parameters in each of `splits` gradient slabs  */
+/* (offsets in floats from the slab start) and zeroes the folded layer's gradient.  `scratch`:  */
+/* rb200_dueling_scratch_floats(H, splits) floats of device memory.                             */
 /* ------------------------------------------------------------------------- */
+int64_t rb200_dueling_scratch_floats(int32_t head_hidden, int32_t splits);
 int rb200_dueling_fold(const float* W_adv, const float* b_adv, const float* w_val,
-                       const float* b_val, int32_t num_actions, int32_t head_hidden, float* W_q,
-                       float* b_q, void* stream);
+                       const float* b_val, int32_t num_actions, int32_t num_atoms,
+                       int32_t head_hidden, float* W_q, float* b_q, float* scratch, void* stream);
 int rb200_dueling_unfold(float* grad, int64_t slab_stride, int32_t splits, int32_t num_actions,
-                         int32_t head_hidden, int64_t off_W_q, int64_t off_b_q, int64_t off_W_adv,
-                         int64_t off_b_adv, int64_t off_w_val, int64_t off_b_val, void* stream);
+                         int32_t num_atoms, int32_t head_hidden, int64_t off_W_q, int64_t off_b_q,
+                         int64_t off_W_adv, int64_t off_b_adv, int64_t off_w_val,
+                         int64_t off_b_val, float* scratch, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* K2 (+K2'): fused DQN TD-target / loss / backward over row tiles.            */

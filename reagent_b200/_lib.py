@@ -187,9 +187,13 @@ def _declare(lib):
     lib.rb200_num_row_tiles.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.rb200_dqn_td_step.argtypes = [C.POINTER(MlpT), C.POINTER(MlpT), C.POINTER(DqnArgsT),
                                       C.POINTER(NetWsT), _vp]
-    lib.rb200_dueling_fold.argtypes = [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp]
-    lib.rb200_dueling_unfold.argtypes = [_vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
-                                         C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp]
+    lib.rb200_dueling_scratch_floats.argtypes = [C.c_int32, C.c_int32]
+    lib.rb200_dueling_scratch_floats.restype = C.c_int64
+    lib.rb200_dueling_fold.argtypes = [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp,
+                                       _vp, _vp]
+    lib.rb200_dueling_unfold.argtypes = [_vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                         C.c_int64, _vp, _vp]
     lib.rb200_dqn_tc_workspace_bytes.argtypes = [C.POINTER(MlpT), C.c_int32, C.c_int32]
     lib.rb200_dqn_tc_workspace_bytes.restype = C.c_int64
     lib.rb200_dqn_tc_pack.argtypes = [C.POINTER(MlpT), C.POINTER(MlpT), C.c_int32, C.c_int32, _vp,

@@ -9,8 +9,8 @@ from typing import Union, Dict, List, Optional
 
 from ..core.parameters import (EvaluationParameters, NormalizationData, NormalizationKey,
                                RLParameters)
-from ..net_builder import (ActorFullyConnected, Dueling, FullyConnected, GaussianFullyConnected,
-                           ParametricFullyConnected, Quantile)
+from ..net_builder import (ActorFullyConnected, Dueling, DuelingQuantile, FullyConnected,
+                           GaussianFullyConnected, ParametricFullyConnected, Quantile)
 from ..optimizer import Optimizer__Union
 from ..training import DQNTrainer, QRDQNTrainer, SACTrainer, TD3Trainer
 
@@ -76,7 +76,8 @@ class DiscreteQRDQN(_DiscretePolicyMixin):
     num_atoms: int = 51
     minibatch_size: int = 1024
     optimizer: Optimizer__Union = field(default_factory=Optimizer__Union.default)
-    net_builder: Quantile = field(default_factory=Quantile)
+    # reagent/model_managers/discrete/discrete_qrdqn.py:39-43: the reference defaults to DuelingQuantile
+    net_builder: Union[DuelingQuantile, Quantile] = field(default_factory=DuelingQuantile)
     eval_parameters: EvaluationParameters = field(
         default_factory=lambda: EvaluationParameters(calc_cpe_in_training=False))
 

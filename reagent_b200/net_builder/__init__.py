@@ -62,6 +62,23 @@ class Quantile:
 
 
 @dataclass
+class DuelingQuantile:
+    """reagent/net_builder/quantile_dqn/dueling_quantile.py:16-40"""
+    sizes: List[int] = field(default_factory=lambda: [256, 128])
+    activations: List[str] = field(default_factory=lambda: ["relu", "relu"])
+
+    def __post_init__(self):
+        assert len(self.sizes) == len(self.activations), (
+            f"Must have the same numbers of sizes and activations; got: {self.sizes}, {self.activations}")
+
+    def build_q_network(self, state_normalization_data: NormalizationData, output_dim: int,
+                        num_atoms: int):
+        return DuelingQNetwork.make_fully_connected(
+            _dim(state_normalization_data), output_dim, layers=self.sizes,
+            activations=self.activations, num_atoms=num_atoms)
+
+
+@dataclass
 class ParametricFullyConnected:
     """reagent/net_builder/parametric_dqn/fully_connected.py:16-54 (the SAC / TD3 critics)"""
     sizes: List[int] = field(default_factory=lambda: [128, 64])

@@ -127,6 +127,8 @@ class QRDQNTrainer(DQNTrainerBaseLightning):
         if qa.dims[-1] != self.num_actions * self.num_atoms:
             raise ValueError("q_network output width must be num_actions * num_atoms")
         lib, st = _lib.lib(), _lib.cur_stream()
+        qa.refresh()  # no-op for plain MLPs; folds a dueling head into its last Linear
+        ta.refresh()
         if self.double_q_learning and self.maxq_learning:
             self._forward(qa, next_state, ws["q_next_online"], ws, save=False)
         self._forward(ta, next_state, ws["q_next_target"], ws, save=False)
@@ -178,6 +180,7 @@ class QRDQNTrainer(DQNTrainerBaseLightning):
                                             ws["net"].c, st)
                 _lib.check(rc, "rb200_mlp_backward")
         wgrad(qa, ws["net"], state, B)
+        qa.finish_grads()  # dueling: folded-layer gradient -> true parameters
         self.all_q_values = ws["all_q"]
         return ws["loss"].reshape(())
 

@@ -165,9 +165,9 @@ def test_td3_oracle_matches_reference(name):
         _cmp_net(st.q2t, arrays, "q2t_N", 1e-5)
 
 
-QRDQN_CASES = ["qrdqn_double", "qrdqn_single_masked", "qrdqn_sarsa_multistep"]
+QRDQN_CASES = ["qrdqn_double", "qrdqn_single_masked", "qrdqn_sarsa_multistep", "qrdqn_dueling"]
 # oracle-only for now: the dueling quantile head has no CUDA path yet (SURVEY M6 / config 3 note)
-QRDQN_ORACLE_ONLY = ["qrdqn_dueling"]
+QRDQN_ORACLE_ONLY = []
 
 
 @pytest.mark.parametrize("name", QRDQN_CASES + QRDQN_ORACLE_ONLY)

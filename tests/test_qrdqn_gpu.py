@@ -14,11 +14,15 @@ TOL = 1e-5
 
 def _build(meta, arrays):
     from reagent_b200.core.parameters import EvaluationParameters, RLParameters
-    from reagent_b200.models import FullyConnectedDQN
+    from reagent_b200.models import DuelingQNetwork, FullyConnectedDQN
     from reagent_b200.optimizer import Optimizer__Union
     from reagent_b200.training import QRDQNTrainer
 
-    q = FullyConnectedDQN(meta["S"], meta["A"], meta["sizes"], meta["acts"], num_atoms=meta["N"])
+    if meta.get("dueling"):
+        q = DuelingQNetwork.make_fully_connected(meta["S"], meta["A"], meta["sizes"], meta["acts"],
+                                                 num_atoms=meta["N"])
+    else:
+        q = FullyConnectedDQN(meta["S"], meta["A"], meta["sizes"], meta["acts"], num_atoms=meta["N"])
     qt = q.get_target_network()
     G.load_into_module(arrays, "q0", q)
     G.load_into_module(arrays, "qt0", qt)
@@ -68,11 +72,34 @@ def test_qrdqn_matches_reference(name, fast):
         else:
             loss = float(run_update(t, batch, it)[0].detach())
         assert abs(loss - ref) <= TOL * max(1.0, abs(ref)), (it, loss, ref)
-    for i, seq in enumerate(t.q_network.fc.dnn):
-        assert G.rel_err(seq[0].weight, arrays[f"qN.W{i}"]) < TOL
-        assert G.rel_err(seq[0].bias, arrays[f"qN.b{i}"]) < TOL
-    for i, seq in enumerate(t.q_network_target.fc.dnn):
-        assert G.rel_err(seq[0].weight, arrays[f"qtN.W{i}"]) < TOL
+    for net, prefix in ((t.q_network, "qN"), (t.q_network_target, "qtN")):
+        ps = list(net.parameters())  # dueling: shared, advantage, value (reference order)
+        pairs = G.net_pairs(arrays, prefix)
+        assert len(ps) == 2 * len(pairs)
+        for i, (w, b) in enumerate(pairs):
+            assert G.rel_err(ps[2 * i], w) < TOL, (prefix, i)
+            assert G.rel_err(ps[2 * i + 1], b) < TOL, (prefix, i)
+
+
+def test_dueling_quantile_forward_matches_reference():
+    """DuelingQNetwork with atoms: (B, A, N) output, mean over actions AND atoms
+    (dueling_q_network.py:92-103); the manager default is DuelingQuantile as in the reference."""
+    from reagent_b200.core import types as rlt
+    from reagent_b200.model_managers import DiscreteQRDQN
+    from reagent_b200.net_builder import DuelingQuantile
+
+    arrays, meta = G.load("qrdqn_dueling")
+    t = _build(meta, arrays)
+    x = rlt.FeatureData(torch.from_numpy(arrays["batch.state"]).cuda())
+    out = t.q_network(x)
+    B, A, N = meta["B"], meta["A"], meta["N"]
+    assert out.shape == (B, A, N)
+    value, raw_adv, adv, qv = t.q_network._get_values(x)
+    assert value.shape == (B, 1, N) and raw_adv.shape == (B, A, N)
+    assert G.rel_err(qv, out) < TOL
+    assert float(adv.mean(dim=(1, 2)).abs().max()) < 1e-6
+    assert G.rel_err(out.mean(dim=2), arrays["all_q0"]) < TOL
+    assert isinstance(DiscreteQRDQN().net_builder, DuelingQuantile)
 
 
 def _qrdqn_oracle_chunked(qo, qt, b, *, gamma, num_atoms, chunk=256):
