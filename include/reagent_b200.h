@@ -446,6 +446,63 @@ int rb200_valid_index_build(const uint8_t* valid, int64_t capacity, int32_t* cou
                             int32_t* offsets, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* Device-resident replay bookkeeping (rb200_replay_dev.cu): the online loop "add a      */
+/* transition -> draw a prioritized minibatch -> train" without host work per step.     */
+/*   rb200_replay_add_device  n consecutive ReplayBuffer.add() calls, stack_size == 1    */
+/*       (circular_replay_buffer.py:468-547; validity :430-438; PER priority ->          */
+/*       SumTree.set, prioritized_replay_buffer.py:62-84) from device staging rows        */
+/*   rb200_sumtree_set_device PrioritizedReplayBuffer.set_priority: SumTree.set for a     */
+/*       batch applied IN ORDER (sum_tree.py:164-189), fp64, bit-equal to the host heap   */
+/*   rb200_per_draw_indices   sample_index_batch of the prioritized buffer                */
+/*       (prioritized_replay_buffer.py:86-115): B stratified random.uniform draws from a  */
+/*       DEVICE copy of CPython's MT19937 state (624 words + position, as                 */
+/*       random.getstate()[1] lays them out), the tree descents, and the sequential       */
+/*       non-stratified retries of invalid hits with the shared attempt budget.           */
+/* status words are sticky error flags the host wrapper turns into the reference's        */
+/* exceptions: 1 = "Max sample attempts", 2 = negative priority.                          */
+/* ------------------------------------------------------------------------- */
+typedef struct rb200_replay_dev {
+  int64_t* state;             /* [4] device: add_count, transitions in the current episode,
+                                 number of valid indices, sticky error */
+  int32_t capacity, update_horizon;
+  uint8_t* valid;             /* [capacity] */
+  uint8_t* terminal;          /* [capacity] */
+  float* reward;              /* [capacity] */
+  double* tree;               /* fp64 heap (level l at [2^l-1, 2^(l+1)-1)) or NULL */
+  int32_t tree_depth;
+  double* max_priority;       /* [1] SumTree.max_recorded_priority or NULL */
+} rb200_replay_dev_t;
+
+typedef struct rb200_add_args {
+  rb200_replay_dev_t rb;
+  int32_t n;                          /* transitions in this call, <= 1024 */
+  const uint8_t* terminal_in;         /* [n] */
+  const float* reward_in;             /* [n] */
+  const double* priority_in;          /* [n] or NULL */
+  int32_t n_rows;                     /* other keys: src = staging [n,row_bytes], dst = store */
+  rb200_gather_spec_t rows[RB200_MAX_GATHER_SPECS];
+} rb200_add_args_t;
+
+typedef struct rb200_per_draw_args {
+  uint32_t* mt_state;         /* [625] device, updated in place */
+  int32_t batch;
+  const double* lo;           /* [B] np.linspace(0,1,B+1)[:-1] */
+  const double* hi;           /* [B] np.linspace(0,1,B+1)[1:]  */
+  const double* tree;
+  int32_t tree_depth;
+  const uint8_t* valid;       /* [capacity] */
+  int32_t max_attempts;
+  int64_t* indices_out;       /* [B] */
+  double* queries_out;        /* [B] or NULL */
+  int32_t* status;            /* [2]: sticky error, retries used by this call */
+} rb200_per_draw_args_t;
+
+int rb200_replay_add_device(const rb200_add_args_t* args, void* stream);
+int rb200_sumtree_set_device(double* tree, int32_t depth, const int64_t* idx, const double* val,
+                             int32_t n, double* max_recorded, int32_t* status, void* stream);
+int rb200_per_draw_indices(const rb200_per_draw_args_t* args, void* stream);
+
+/* ------------------------------------------------------------------------- */
 /* Peer-memory plumbing of the fused data-parallel step (one process per GPU).  The    */
 /* reference has no collective on this path (docs/distributed.rst:12-22 states the     */
 /* intent: synchronous data parallelism with a gradient all-reduce).                   */

@@ -155,6 +155,24 @@ class SampleArgsT(C.Structure):
     ]
 
 
+class ReplayDevT(C.Structure):
+    _fields_ = [("state", _vp), ("capacity", C.c_int32), ("update_horizon", C.c_int32),
+                ("valid", _vp), ("terminal", _vp), ("reward", _vp), ("tree", _vp),
+                ("tree_depth", C.c_int32), ("max_priority", _vp)]
+
+
+class AddArgsT(C.Structure):
+    _fields_ = [("rb", ReplayDevT), ("n", C.c_int32), ("terminal_in", _vp), ("reward_in", _vp),
+                ("priority_in", _vp), ("n_rows", C.c_int32),
+                ("rows", GatherSpecT * MAX_GATHER_SPECS)]
+
+
+class PerDrawArgsT(C.Structure):
+    _fields_ = [("mt_state", _vp), ("batch", C.c_int32), ("lo", _vp), ("hi", _vp), ("tree", _vp),
+                ("tree_depth", C.c_int32), ("valid", _vp), ("max_attempts", C.c_int32),
+                ("indices_out", _vp), ("queries_out", _vp), ("status", _vp)]
+
+
 class QrdqnArgsT(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("num_actions", C.c_int32), ("num_atoms", C.c_int32),
@@ -233,6 +251,9 @@ def _declare(lib):
     lib.rb200_grad_reduce.argtypes = [_vp, C.c_int32, C.c_int64, _vp, _vp]
     lib.rb200_adam_soft_update.argtypes = [C.POINTER(AdamArgsT), _vp]
     lib.rb200_soft_update.argtypes = [_vp, _vp, C.c_int64, C.c_float, C.c_float, _vp]
+    lib.rb200_replay_add_device.argtypes = [C.POINTER(AddArgsT), _vp]
+    lib.rb200_sumtree_set_device.argtypes = [_vp, C.c_int32, _vp, _vp, C.c_int32, _vp, _vp, _vp]
+    lib.rb200_per_draw_indices.argtypes = [C.POINTER(PerDrawArgsT), _vp]
     lib.rb200_adam_blocks.argtypes = [C.c_int64]
     lib.rb200_dp_alloc.argtypes = [C.c_int64, C.POINTER(_vp)]
     lib.rb200_dp_free.argtypes = [_vp]

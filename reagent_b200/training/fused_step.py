@@ -26,11 +26,26 @@ from ..replay_memory.prioritized_replay_buffer import PrioritizedReplayBuffer
 
 class FusedDqnStep:
     def __init__(self, trainer, replay_buffer, batch_size: int, process_group=None,
-                 slots: int = 2, prefetch: bool = False, shard=None):
+                 slots: int = 2, prefetch: bool = False, shard=None, rng: str = "host",
+                 online: bool = False):
         """`shard = (rank, world)`: data-parallel strong scaling.  `batch_size`
         is the GLOBAL minibatch; the replay buffer is replicated and every rank consumes the
-        identical host random stream, so all ranks select the same global indices, and this
-        rank gathers and trains on rows [rank*B/world, (rank+1)*B/world) only."""
+        identical random stream, so all ranks select the same global indices, and this
+        rank gathers and trains on rows [rank*B/world, (rank+1)*B/world) only.
+
+        `rng="device"` (prioritized buffer): the buffer goes device-resident
+        (replay_memory/device_replay.py) -- Python's `random` state is uploaded once and the
+        stratified draws, tree descents and retries of sample_index_batch run in a kernel
+        inside the captured graph: no host random numbers, no per-step query upload.
+        `online=True` (needs rng="device"): `step(transition)` also ADDS one transition before
+        drawing, the reference's online loop (reagent/gym/runners/gymrunner.py: one env step
+        -> replay_buffer.add -> one update); the transition is the step's only host->device
+        traffic, staged in pinned memory and copied + inserted by the same graph replay."""
+        if rng not in ("host", "device"):
+            raise ValueError("rng must be 'host' or 'device'")
+        if online and rng != "device":
+            raise ValueError("online=True needs rng='device' (device-resident replay)")
+        self.rng, self.online = rng, bool(online)
         self.trainer = trainer
         self.rb = replay_buffer
         self.B_global = batch_size
@@ -53,6 +68,20 @@ class FusedDqnStep:
         self.d2h_bytes = 4
         self.prefetch = bool(prefetch)
         replay_buffer._flush()
+        self.dr = None
+        if rng == "device":
+            from ..replay_memory.device_replay import DeviceReplay
+
+            if not self.prioritized:
+                raise NotImplementedError("rng='device' covers the prioritized buffer")
+            self.dr = getattr(replay_buffer, "_device_resident", None) or DeviceReplay(replay_buffer, stage_rows=2)
+            if self.dr.stage_rows < 2:
+                self.dr._alloc_stage(2)
+            self._idx_buf = [torch.zeros(self.B_global, dtype=torch.int64, device=self.dev)
+                             for _ in range(2)]
+            self._status_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+            self.h2d_bytes = self.dr.h2d_bytes_per_row if self.online else 0
+            self.d2h_bytes = 4 + 8
         # warm-up outside capture (lazy allocations, cudaFuncSetAttribute, optimizer state)
         self._one_update(None)
         torch.cuda.synchronize()
@@ -100,7 +129,9 @@ class FusedDqnStep:
             with torch.cuda.stream(self._side2):
                 forked = prepack()
         with torch.cuda.stream(self._side), self.rb.output_buffers(self._pools[1 - i]):
-            if overrides is None:
+            if self.dr is not None:
+                nxt = self._device_sample(1 - i, self.online and rnd_dev is not None, stage_row=i)
+            elif overrides is None:
                 nxt = self._sample(rnd_dev)
             else:
                 nxt = self.rb.sample_discrete_dqn_batch(self.B, self.A, query_dev=rnd_dev,
@@ -124,7 +155,18 @@ class FusedDqnStep:
             raise RuntimeError(f"Cannot sample {self.B_global} since there are no valid indices so far.")
         return torch.randint(n_valid, (self.B_global,))[lo:hi].numpy(), [], []
 
+    def _device_sample(self, slot: int, add: bool, stage_row: int = 0):
+        """Device-resident draw: (optionally insert the staged transition,) select the global
+        indices with the device MT19937 stream, gather this rank's rows."""
+        if add:
+            self.dr.launch_add(1, row0=stage_row)
+        idx = self.dr.draw_indices(self.B_global, out=self._idx_buf[slot])
+        return self.rb.sample_discrete_dqn_batch(self.B, self.A,
+                                                 indices=idx[self.row0:self.row0 + self.B])
+
     def _sample(self, rnd_dev):
+        if self.dr is not None:
+            return self._device_sample(0, False)
         if rnd_dev is None and self.B != self.B_global:
             q, pos, idxs = self._host_draw()
             qd = torch.from_numpy(np.ascontiguousarray(q)).to(self.dev)
@@ -143,7 +185,24 @@ class FusedDqnStep:
             batch = self.rb.sample_discrete_dqn_batch(self.B, self.A, ranks_dev=rnd_dev)
         return batch
 
+    def _capture_device(self, i=0):
+        loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        g = torch.cuda.CUDAGraph()
+        marker = torch.zeros(1, device=self.dev)  # non-None: "inside the captured step"
+        with torch.cuda.graph(g):
+            if self.prefetch:
+                loss = self._prefetch_update(i, marker)
+            else:
+                if self.online:
+                    self.dr.launch_add(1, row0=i)
+                loss = self.trainer.train_batch(self._device_sample(0, False), process_group=self.pg)
+            loss_host.copy_(loss.reshape(1), non_blocking=True)
+            self._status_host.copy_(self.dr.status, non_blocking=True)
+        return {"graph": g, "loss_host": loss_host, "done": torch.cuda.Event(), "used": False}
+
     def _capture(self, i=0):
+        if self.dr is not None:
+            return self._capture_device(i)
         dt = torch.float64 if self.prioritized else torch.int64
         host = torch.zeros(self.B, dtype=dt).pin_memory()
         devb = torch.zeros(self.B, dtype=dt, device=self.dev)
@@ -157,14 +216,28 @@ class FusedDqnStep:
                 "done": torch.cuda.Event(), "used": False}
 
     # -- public --------------------------------------------------------------------
-    def step(self) -> torch.Tensor:
+    def step(self, transition=None) -> torch.Tensor:
         """One full update.  Returns the pinned host tensor that will hold the loss once the
         stream reaches the end of this update (call torch.cuda.current_stream().synchronize()
-        or keep going: slots are recycled only after their event completed)."""
+        or keep going: slots are recycled only after their event completed).
+        `transition` (online mode): dict of the add() keyword arguments of the new transition."""
         s = self.slots[self.k % len(self.slots)]
         self.k += 1
         if s["used"]:
             s["done"].synchronize()
+        if self.dr is not None:
+            if self._status_host[0] != 0:  # sticky device status of an earlier step
+                self.dr.raise_if_failed(self._status_host)
+            if self.online:
+                if transition is None:
+                    raise ValueError("online FusedDqnStep.step() needs the new transition")
+                # every slot's graph copies from its own pinned staging row; the slot's previous
+                # replay (and with it that H2D copy) was waited for above
+                self.dr.stage((self.k - 1) % len(self.slots), **transition)
+            s["graph"].replay()
+            s["done"].record()
+            s["used"] = True
+            return s["loss_host"]
         # bring device mirrors up to date OUTSIDE the captured graph (adds / set_priority)
         self.rb._flush()
         if self.prioritized:

@@ -98,7 +98,10 @@ def test_dueling_quantile_forward_matches_reference():
     assert value.shape == (B, 1, N) and raw_adv.shape == (B, A, N)
     assert G.rel_err(qv, out) < TOL
     assert float(adv.mean(dim=(1, 2)).abs().max()) < 1e-6
-    assert G.rel_err(out.mean(dim=2), arrays["all_q0"]) < TOL
+    # against the oracle's dueling forward (pinned to the reference by tests/test_oracle_golden.py)
+    qo = G.oracle_net(arrays, "q0", meta["acts"] + ["linear"])
+    want = O.mlp(qo, torch.from_numpy(arrays["batch.state"]))
+    assert G.rel_err(out.reshape(B, -1), want) < TOL
     assert isinstance(DiscreteQRDQN().net_builder, DuelingQuantile)
 
 
