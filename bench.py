@@ -187,6 +187,8 @@ def _cpu_setup(cfg):
     ro.bulk_fill(synth_stream(cap, 1000, cfg))
     gen = torch.Generator().manual_seed(0)
     algo = cfg["algo"]
+    extra = synth_stream(256, 555, cfg) if algo == "dqn" else None
+    it = [0]
     if algo in ("dqn", "qrdqn"):
         out = Ac * (cfg.get("N", 1))
         q = O.make_net([Sc] + cfg["sizes"] + [out], ACTS + ["linear"], gen)
@@ -196,6 +198,10 @@ def _cpu_setup(cfg):
         adam = O.AdamState(O.net_params(q), lr=LR)
 
         def one():
+            if extra is not None:  # the online loop: one new transition per update
+                i = it[0] % len(extra["terminal"])
+                ro.add(**{k: v[i] for k, v in extra.items()})
+                it[0] += 1
             ob = ro.sample_transition_batch(Bc)
             term = torch.from_numpy(ob["terminal"])
             batch = dict(
@@ -265,7 +271,7 @@ def cpu_reference_run(steps, warmup, cfg=None, threads=None):
         one()
     dt = time.perf_counter() - t0
     return (steps / dt, cores,
-            f"{steps} full updates (PER sample B={cfg['B']} + {cfg['algo']} update) after "
+            f"{steps} full updates ({'1 replay add + ' if cfg['algo'] == 'dqn' else ''}PER sample B={cfg['B']} + {cfg['algo']} update) after "
             f"{warmup} warm-up; torch threads={cores} (best of a sweep over <= {os.cpu_count()} cores)",
             dt / steps * 1e3)
 
@@ -498,22 +504,43 @@ def run_dqn(env, args, clocks):
 
     check = dp_check(env, cfg, rb) if world > 1 else None
 
-    # ---- e2e: public API, host RNG -> pinned -> H2D, loss D2H every update ----
+    def timed_loop(step_fn):
+        for i in range(W):
+            step_fn(i)
+        env.barrier()
+        clocks.mark()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(K):
+            lh = step_fn(W + i)
+        e1.record()
+        env.barrier()
+        t_host = time.perf_counter() - t0
+        return env.max_over_ranks(max(e0.elapsed_time(e1), t_host * 1e3)), float(lh[0])
+
+    # ---- e2e, host random numbers: host RNG -> pinned -> H2D (B*8 bytes), loss D2H ----
     fused = FusedDqnStep(trainer, rb, Bg, process_group=pg, prefetch=True, shard=(env.rank, world))
-    for _ in range(W):
-        fused.step()
-    env.barrier()
-    clocks.mark()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_host0 = time.perf_counter()
-    e0.record()
-    for _ in range(K):
-        loss_host = fused.step()
-    e1.record()
-    env.barrier()
-    t_host = time.perf_counter() - t_host0
-    e2e_ms = env.max_over_ranks(max(e0.elapsed_time(e1), t_host * 1e3))
-    last_loss = float(loss_host[0])
+    hostrng_ms, _ = timed_loop(lambda i: fused.step())
+    hostrng = {"value": K / (hostrng_ms * 1e-3), "ms_per_step": hostrng_ms / K,
+               "h2d_bytes_per_step": fused.h2d_bytes, "d2h_bytes_per_step": fused.d2h_bytes,
+               "api": "FusedDqnStep(prefetch=True).step(): the host draws the stratified query "
+                      "values (Python `random`), pinned -> H2D, update, loss D2H"}
+    del fused
+
+    # ---- e2e (headline): the ONLINE loop through the public API.  Every step the host hands
+    # over one new transition (pinned memory -> H2D inside the step), the step inserts it
+    # (device-resident replay: validity + sum-tree update), draws the prioritized minibatch
+    # with the device copy of Python's MT19937 stream (same indices as the reference), trains,
+    # and copies the loss + status back -- one CUDA-graph replay per step ----
+    extra = synth_stream(W + K + 4, 555, cfg)  # the same new transitions on every rank
+    online = FusedDqnStep(trainer, rb, Bg, process_group=pg, prefetch=True,
+                          shard=(env.rank, world), rng="device", online=True)
+    e2e_ms, last_loss = timed_loop(
+        lambda i: online.step({k: v[i] for k, v in extra.items()}))
+    h2d_online, d2h_online = online.h2d_bytes, online.d2h_bytes
+    online.dr.sync_to_host()  # the sections below use the host-side API again
+    del online
 
     # ---- the drop-in surface, un-fused: sample_transition_batch -> InputMaker -> generator
     # protocol under the loop (what a user of the reference's workflow calls) ----
@@ -601,7 +628,7 @@ def run_dqn(env, args, clocks):
     conf = base_config(cfg, world)
     detail = dict(value_path="K updates in one CUDA graph, query values resident in HBM; "
                              "retry-free draws only (PER retries are host logic, timed in e2e)",
-                  final_loss=last_loss, rows_per_rank=Bl)
+                  final_loss=last_loss, rows_per_rank=Bl, e2e_host_rng=hostrng)
     if weak:
         detail["weak"] = weak
     if env.collective:
@@ -615,11 +642,14 @@ def run_dqn(env, args, clocks):
     res = {
         "value": K / (dev_ms * 1e-3), "ms_per_step": dev_ms / K, "config": conf, "detail": detail,
         "e2e": {"value": K / (e2e_ms * 1e-3), "unit": "updates/s",
-                "h2d_bytes_per_step": fused.h2d_bytes, "d2h_bytes_per_step": fused.d2h_bytes,
+                "h2d_bytes_per_step": h2d_online, "d2h_bytes_per_step": d2h_online,
                 "ms_per_step": e2e_ms / K,
-                "api": "reagent_b200.training.fused_step.FusedDqnStep(prefetch=True).step(): every "
-                       "step draws one minibatch (host RNG -> pinned -> H2D -> sample kernel) and "
-                       "trains on one; the sampler runs one update ahead on a second stream"},
+                "api": "reagent_b200.training.fused_step.FusedDqnStep(rng='device', online=True, "
+                       "prefetch=True).step(transition): per step the host stages ONE new "
+                       "transition in pinned memory; the captured step copies it to the device, "
+                       "inserts it into the replay buffer, draws the minibatch (device MT19937 = "
+                       "Python's random stream), trains and returns the loss; the sampler runs one "
+                       "update ahead on a second stream"},
         # sample, (weight images unless Adam wrote them), TD step, weight gradients, Adam+Polyak
         "gpu_launches": (4 if (not on_tc or os.environ.get("RB200_ADAM_PACK", "1") == "1") else 5) * K,
         "roofline_kernel": {

@@ -11,10 +11,11 @@
 //
 // HBM-bound.  Algorithmic bytes per sampled transition:
 //   d*8 (fp64 tree nodes) + 2*S*4 read + 2*S'*4 written + ~13 read + ~40 scalar outputs.
-// Layout: one CTA = 32 samples.  Warp 0 does the 32 index selections in lock-step (one
-// dependent 8-byte load per tree level per lane); then all 8 warps stream the rows: a warp
-// copies one 4*S-byte observation row with coalesced 16-byte loads, normalises in registers
-// and writes the output row coalesced.
+// Layout: one CTA = 32 samples, 4 per warp.  Lane u of a warp does the index selection and the
+// scalar outputs of the warp's sample u (one dependent 8-byte load per deep tree level), so a
+// CTA's 32 descents run in 8 warps whose latencies overlap; then the warp streams its 8 rows
+// (state and next_state of 4 samples): all row loads are issued (coalesced 16-byte loads, one
+// 512-byte request per row) before the first store.
 #include "rb200_preproc.cuh"
 
 namespace rb200 {
@@ -33,9 +34,6 @@ __device__ __forceinline__ long long wrap(long long i, long long cap) {
 
 __global__ void __launch_bounds__(kThreads) replay_sample_kernel(const SampleDev d) {
   const rb200_sample_args_t& a = d.a;
-  __shared__ long long s_idx[kSPB];
-  __shared__ long long s_next[kSPB];
-  __shared__ int s_term[kSPB];
   // top kTopLevels levels of the fp64 sum tree (2^kTopLevels - 1 nodes, 8 KB): loaded once
   // per CTA with coalesced reads so that only the deep levels cost a dependent L2 round trip
   __shared__ double s_top[(1 << kTopLevels) - 1];
@@ -49,10 +47,16 @@ __global__ void __launch_bounds__(kThreads) replay_sample_kernel(const SampleDev
     __syncthreads();
   }
 
-  if (warp == 0) {
-    const int b = b0 + lane;
-    if (b < a.batch) {
-      long long idx = 0;
+  // ---- index selection + scalar outputs: every warp owns kPerWarp samples, lane u does the
+  // scalar work of sample u, so the 32 descents of a CTA run in 8 warps whose dependent loads
+  // overlap (one warp doing all 32 in lock-step left 7 warps idle) ----
+  constexpr int kPerWarp = kSPB / (kThreads / 32);  // 4
+  long long idx = 0, next = 0;
+  int term = 0;
+  long long act = 0, nact = 0;
+  {
+    const int b = b0 + warp * kPerWarp + lane;
+    if (lane < kPerWarp && b < a.batch) {
       if (a.mode == RB200_SAMPLE_PRIORITIZED) {
         // sum_tree.py:112-131: q *= root; descend comparing with the left child
         double q = a.query[b] * s_top[0];
@@ -104,11 +108,8 @@ __global__ void __launch_bounds__(kThreads) replay_sample_kernel(const SampleDev
         const float m = (k < steps) ? 1.f : 0.f;
         rew += __fmul_rn(__fmul_rn(a.reward[wrap(idx + k, cap)], a.decays[k]), m);
       }
-      const long long next = a.timeline_next ? wrap(idx + 1, cap) : wrap(idx + steps, cap);
-      const int term = a.terminal[wrap(idx + steps - 1, cap)] ? 1 : 0;  // :658-660
-      s_idx[lane] = idx;
-      s_next[lane] = next;
-      s_term[lane] = term;
+      next = a.timeline_next ? wrap(idx + 1, cap) : wrap(idx + steps, cap);
+      term = a.terminal[wrap(idx + steps - 1, cap)] ? 1 : 0;  // :658-660
       if (a.indices_out) a.indices_out[b] = idx;
       if (a.step_out) a.step_out[b] = steps;
       if (a.step_f32_out) a.step_f32_out[b] = (float)steps;
@@ -119,61 +120,97 @@ __global__ void __launch_bounds__(kThreads) replay_sample_kernel(const SampleDev
       if (a.sampling_prob_out)  // prioritized_replay_buffer.py:136-140 (get_priority -> f32)
         a.sampling_prob_out[b] = (float)a.tree[((1ll << a.tree_depth) - 1) + idx];
       if (a.action_i64) {
-        const long long act = a.action_i64[idx];
-        const long long nact = a.action_i64[next];
+        act = a.action_i64[idx];
+        nact = a.action_i64[next];
         if (a.action_out_i64) a.action_out_i64[b] = act;
         if (a.next_action_out_i64) a.next_action_out_i64[b] = nact;
-        if (a.action_onehot) {  // one_hot_actions, trainer_preprocessor.py:72-97
-          for (int c = 0; c < a.num_actions; ++c) {
-            a.action_onehot[(size_t)b * a.num_actions + c] = (c == act) ? 1.f : 0.f;
-            a.next_action_onehot[(size_t)b * a.num_actions + c] = (!term && c == nact) ? 1.f : 0.f;
-          }
-        }
       }
-    } else {
-      s_idx[lane] = 0;
-      s_next[lane] = 0;
-      s_term[lane] = 0;
     }
   }
-  __syncthreads();
 
-  // ---- row gathers: warp w streams samples w, w+8, w+16, w+24 ----
-  for (int s = warp; s < kSPB; s += kThreads / 32) {
-    const int b = b0 + s;
-    if (b >= a.batch) break;
-    const long long idx = s_idx[s], next = s_next[s];
-    const int term = s_term[s];
-    // observation -> state / next_state (with optional normalisation)
-    if (a.obs) {
-      for (int which = 0; which < 2; ++which) {
-        float* dst = which ? a.next_state : a.state;
-        if (!dst) continue;
-        const float* src = a.obs + (size_t)(which ? next : idx) * a.obs_dim;
-        if (a.cols == nullptr) {
-          const bool vec = ((a.obs_dim & 3) == 0) &&
-                           ((reinterpret_cast<uintptr_t>(a.obs) & 15) == 0) &&
-                           ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-          float* drow = dst + (size_t)b * a.obs_dim;
-          if (vec) {
-            for (int c = lane * 4; c < a.obs_dim; c += 128)
-              *reinterpret_cast<float4*>(drow + c) = __ldg(reinterpret_cast<const float4*>(src + c));
+  // ---- row gathers: the warp streams its kPerWarp samples ----
+  long long s_idx[kPerWarp], s_next[kPerWarp];
+  int s_term[kPerWarp];
+#pragma unroll
+  for (int u = 0; u < kPerWarp; ++u) {
+    s_idx[u] = __shfl_sync(0xffffffffu, idx, u);
+    s_next[u] = __shfl_sync(0xffffffffu, next, u);
+    s_term[u] = __shfl_sync(0xffffffffu, term, u);
+  }
+  const int bw = b0 + warp * kPerWarp;  // first sample of this warp
+  // one-hot actions (one_hot_actions, trainer_preprocessor.py:72-97): lanes over the actions
+  if (a.action_i64 && a.action_onehot) {
+#pragma unroll
+    for (int u = 0; u < kPerWarp; ++u) {
+      const long long au = __shfl_sync(0xffffffffu, act, u), nu = __shfl_sync(0xffffffffu, nact, u);
+      if (bw + u >= a.batch) continue;
+      for (int c = lane; c < a.num_actions; c += 32) {
+        a.action_onehot[(size_t)(bw + u) * a.num_actions + c] = (c == au) ? 1.f : 0.f;
+        a.next_action_onehot[(size_t)(bw + u) * a.num_actions + c] = (!s_term[u] && c == nu) ? 1.f : 0.f;
+      }
+    }
+  }
+  // observation -> state / next_state (with optional normalisation)
+  if (a.obs) {
+    const bool vec = (a.cols == nullptr) && ((a.obs_dim & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(a.obs) & 15) == 0) &&
+                     (!a.state || (reinterpret_cast<uintptr_t>(a.state) & 15) == 0) &&
+                     (!a.next_state || (reinterpret_cast<uintptr_t>(a.next_state) & 15) == 0);
+    if (vec && a.obs_dim <= 128) {
+      // all 2*kPerWarp row loads of the warp are issued before the first store: 8 independent
+      // 512-byte requests in flight per warp instead of one
+      float4 v[2 * kPerWarp];
+      const int c = lane * 4;
+#pragma unroll
+      for (int u = 0; u < kPerWarp; ++u) {
+        const bool on = bw + u < a.batch && c < a.obs_dim;
+        v[2 * u] = (on && a.state) ? __ldg(reinterpret_cast<const float4*>(a.obs + (size_t)s_idx[u] * a.obs_dim + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[2 * u + 1] = (on && a.next_state) ? __ldg(reinterpret_cast<const float4*>(a.obs + (size_t)s_next[u] * a.obs_dim + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < kPerWarp; ++u) {
+        if (bw + u >= a.batch || c >= a.obs_dim) continue;
+        if (a.state) *reinterpret_cast<float4*>(a.state + (size_t)(bw + u) * a.obs_dim + c) = v[2 * u];
+        if (a.next_state) *reinterpret_cast<float4*>(a.next_state + (size_t)(bw + u) * a.obs_dim + c) = v[2 * u + 1];
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < kPerWarp; ++u) {
+        const int b = bw + u;
+        if (b >= a.batch) continue;
+        for (int which = 0; which < 2; ++which) {
+          float* dst = which ? a.next_state : a.state;
+          if (!dst) continue;
+          const float* src = a.obs + (size_t)(which ? s_next[u] : s_idx[u]) * a.obs_dim;
+          if (a.cols == nullptr) {
+            float* drow = dst + (size_t)b * a.obs_dim;
+            if (vec) {
+              for (int c = lane * 4; c < a.obs_dim; c += 128)
+                *reinterpret_cast<float4*>(drow + c) = __ldg(reinterpret_cast<const float4*>(src + c));
+            } else {
+              for (int c = lane; c < a.obs_dim; c += 32) drow[c] = src[c];
+            }
           } else {
-            for (int c = lane; c < a.obs_dim; c += 32) drow[c] = src[c];
-          }
-        } else {
-          float* drow = dst + (size_t)b * a.obs_out_dim;
-          for (int j = lane; j < a.obs_out_dim; j += 32) {
-            const rb200_feature_col_t f = a.cols[j];
-            drow[j] = preprocess_value(src[f.src_col], 1.f, f, a.quantiles);
+            float* drow = dst + (size_t)b * a.obs_out_dim;
+            for (int j = lane; j < a.obs_out_dim; j += 32) {
+              const rb200_feature_col_t f = a.cols[j];
+              drow[j] = preprocess_value(src[f.src_col], 1.f, f, a.quantiles);
+            }
           }
         }
       }
     }
+  }
+#pragma unroll
+  for (int u = 0; u < kPerWarp; ++u) {
+    const int b = bw + u;
+    if (b >= a.batch) continue;
+    const long long idx_u = s_idx[u], next_u = s_next[u];
+    const int term_u = s_term[u];
     // continuous action -> rescaled action / next_action (PolicyNetworkInputMaker :176-196)
     if (a.action_f32) {
-      const float* sa = a.action_f32 + (size_t)idx * a.action_dim;
-      const float* sn = a.action_f32 + (size_t)next * a.action_dim;
+      const float* sa = a.action_f32 + (size_t)idx_u * a.action_dim;
+      const float* sn = a.action_f32 + (size_t)next_u * a.action_dim;
       for (int c = lane; c < a.action_dim; c += 32) {
         float va = sa[c], vn = sn[c];
         if (a.action_out_raw) a.action_out_raw[(size_t)b * a.action_dim + c] = va;
@@ -185,8 +222,8 @@ __global__ void __launch_bounds__(kThreads) replay_sample_kernel(const SampleDev
           a.action_rescaled[(size_t)b * a.action_dim + c] =
               __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(va, lo), range), nr), a.train_low);
           a.next_action_rescaled[(size_t)b * a.action_dim + c] =
-              term ? 0.f
-                   : __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(vn, lo), range), nr), a.train_low);
+              term_u ? 0.f
+                     : __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(vn, lo), range), nr), a.train_low);
         }
       }
     }
@@ -194,7 +231,7 @@ __global__ void __launch_bounds__(kThreads) replay_sample_kernel(const SampleDev
     for (int g = 0; g < a.n_specs; ++g) {
       const rb200_gather_spec_t& sp = a.specs[g];
       const unsigned char* src =
-          (const unsigned char*)sp.src + (size_t)(sp.which ? next : idx) * sp.row_bytes;
+          (const unsigned char*)sp.src + (size_t)(sp.which ? next_u : idx_u) * sp.row_bytes;
       unsigned char* dst = (unsigned char*)sp.dst + (size_t)b * sp.row_bytes;
       if (((sp.row_bytes & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0) &&
           ((reinterpret_cast<uintptr_t>(dst) & 3) == 0)) {

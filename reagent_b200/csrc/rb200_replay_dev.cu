@@ -87,7 +87,8 @@ __device__ __forceinline__ long long tree_walk(const double* __restrict__ tree, 
 
 constexpr int kDrawThreads = 1024;
 constexpr int kDrawTop = 10;       // tree levels cached in shared memory (8 KB)
-constexpr int kDrawChunk = 2048;   // strata per pass (16 KB of raw outputs)
+constexpr int kDrawChunk = 4096;   // strata per pass (32 KB of raw outputs)
+constexpr int kDrawPer = kDrawChunk / kDrawThreads;  // descents per thread, interleaved
 
 struct DrawDev {
   rb200_per_draw_args_t a;
@@ -120,17 +121,50 @@ __global__ void __launch_bounds__(kDrawThreads) per_draw_indices_kernel(const Dr
       produced += take;
       __syncthreads();
     }
-    // ---- stratified queries (sum_tree.py:149-152) and their descents ----
-    for (int i = tid; i < m; i += kDrawThreads) {
-      const int b = base + i;
-      const double r = mt_double(s_raw[2 * i], s_raw[2 * i + 1]);
-      // random.uniform(lo, hi) = lo + (hi - lo) * random(): separately rounded operations
-      const double lo = a.lo[b], hi = a.hi[b];
-      const double q = __dadd_rn(lo, __dmul_rn(__dadd_rn(hi, -lo), r));
-      if (a.queries_out) a.queries_out[b] = q;
-      const long long idx = tree_walk(a.tree, s_top, top, a.tree_depth, __dmul_rn(q, root));
-      a.indices_out[b] = idx;
-      if (!a.valid[idx]) any_invalid = true;
+    // ---- stratified queries (sum_tree.py:149-152) and their descents: each thread walks
+    // kDrawPer strata in lock-step so that their dependent loads overlap ----
+    {
+      double q[kDrawPer];
+      long long node[kDrawPer];
+      int bb[kDrawPer];
+#pragma unroll
+      for (int u = 0; u < kDrawPer; ++u) {
+        const int i = tid + u * kDrawThreads;
+        bb[u] = (i < m) ? base + i : -1;
+        node[u] = 0;
+        q[u] = 0.0;
+        if (bb[u] >= 0) {
+          const double r = mt_double(s_raw[2 * i], s_raw[2 * i + 1]);
+          // random.uniform(lo, hi) = lo + (hi - lo) * random(): separately rounded operations
+          const double lo = a.lo[bb[u]], hi = a.hi[bb[u]];
+          const double qq = __dadd_rn(lo, __dmul_rn(__dadd_rn(hi, -lo), r));
+          if (a.queries_out) a.queries_out[bb[u]] = qq;
+          q[u] = __dmul_rn(qq, root);  // sum_tree.py:113
+        }
+      }
+      for (int lvl = 1; lvl <= a.tree_depth; ++lvl) {
+        double ls[kDrawPer];
+#pragma unroll
+        for (int u = 0; u < kDrawPer; ++u) {
+          const long long p = ((1ll << lvl) - 1) + node[u] * 2;
+          ls[u] = (lvl < top) ? s_top[p] : __ldcg(a.tree + p);
+        }
+#pragma unroll
+        for (int u = 0; u < kDrawPer; ++u) {
+          if (q[u] < ls[u]) {
+            node[u] = node[u] * 2;
+          } else {
+            node[u] = node[u] * 2 + 1;
+            q[u] -= ls[u];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kDrawPer; ++u) {
+        if (bb[u] < 0) continue;
+        a.indices_out[bb[u]] = node[u];
+        if (!a.valid[node[u]]) any_invalid = true;
+      }
     }
     __syncthreads();
   }

@@ -28,7 +28,7 @@ MAX_ADD = 1024  # transitions per rb200_replay_add_device launch
 
 
 class DeviceReplay:
-    def __init__(self, rb, stage_rows: int = 1):
+    def __init__(self, rb, stage_rows: int = 1, stage_slots: int = 1):
         if rb._stack_size != 1:
             raise NotImplementedError("device-resident replay needs stack_size == 1")
         if not rb._initialized_buffer:
@@ -49,23 +49,35 @@ class DeviceReplay:
         self._bounds = {}
         self._keys = [e.name for e in rb.get_add_args_signature()
                       if e.name not in ("terminal", "reward", "priority")]
-        self._alloc_stage(stage_rows)
+        self._alloc_stage(stage_rows, stage_slots)
         rb._device_resident = self
 
     # ---- staging ---------------------------------------------------------------
-    def _alloc_stage(self, rows: int):
+    def _alloc_stage(self, rows: int, slots: int = 1):
+        """`slots` independent staging blocks of `rows` transitions each.  A block is ONE
+        contiguous pinned buffer (key after key, 16-byte aligned), mirrored on the device, so
+        that an add is a single host->device copy however many keys a transition has."""
         rb = self.rb
-        self.stage_rows = rows
-        self.host: Dict[str, torch.Tensor] = {}
-        self.devst: Dict[str, torch.Tensor] = {}
+        self.stage_rows, self.stage_slots = rows, slots
+        self._layout = {}
+        off = 0
         for e in rb.get_add_args_signature():
             md = e.metadata
             if e.name == "priority":
-                dt, shape = torch.float64, [rows]
+                dt, shape = np.dtype(np.float64), ()
             else:
-                dt, shape = md.torch_dtype, [rows, *md.shape]
-            self.host[e.name] = torch.zeros(shape, dtype=dt).pin_memory()
-            self.devst[e.name] = torch.zeros(shape, dtype=dt, device=self.dev)
+                dt, shape = np.dtype(md.dtype), tuple(md.shape)
+            nbytes = rows * int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+            self._layout[e.name] = (off, dt, shape, nbytes)
+            off = (off + nbytes + 15) // 16 * 16
+        self.block_bytes = off
+        self.host_raw = torch.zeros(slots, off, dtype=torch.uint8).pin_memory()
+        self.dev_raw = torch.zeros(slots, off, dtype=torch.uint8, device=self.dev)
+        raw = self.host_raw.numpy()
+        # numpy views of the pinned block: a per-step `stage()` costs ~1 us
+        self.host_np = [{k: raw[sl, o:o + nb].view(dt).reshape((rows,) + shape)
+                         for k, (o, dt, shape, nb) in self._layout.items()}
+                        for sl in range(slots)]
 
     def rb_desc(self) -> _lib.ReplayDevT:
         rb = self.rb
@@ -82,31 +94,27 @@ class DeviceReplay:
             d.max_priority = self.max_priority.data_ptr()
         return d
 
-    def stage(self, row: int, **transition):
-        """Write one transition into row `row` of the pinned staging buffers (host only)."""
+    def stage(self, row: int, slot: int = 0, **transition):
+        """Write one transition into row `row` of staging block `slot` (host only)."""
+        views = self.host_np[slot]
         for k, v in transition.items():
-            self.host[k][row] = torch.as_tensor(v, dtype=self.host[k].dtype) if not isinstance(v, torch.Tensor) else v
+            views[k][row] = v
 
-    def launch_add(self, n: int, row0: int = 0):
-        """H2D copy of staged rows [row0, row0 + n) + the add kernel, on the current stream
-        (graph-capturable: fixed pinned / device staging addresses)."""
-        assert n >= 1 and row0 >= 0 and row0 + n <= self.stage_rows and n <= MAX_ADD
-        for k in self.host:
-            self.devst[k][row0:row0 + n].copy_(self.host[k][row0:row0 + n], non_blocking=True)
-
-        def at(k):
-            t = self.devst[k]
-            return t.data_ptr() + row0 * (t[0].numel() if t.dim() > 1 else 1) * t.element_size()
-
+    def launch_add(self, n: int, slot: int = 0):
+        """ONE host->device copy of staging block `slot` + the add kernel for its first `n`
+        rows, on the current stream (graph-capturable: fixed pinned / device addresses)."""
+        assert 1 <= n <= min(self.stage_rows, MAX_ADD) and 0 <= slot < self.stage_slots
+        self.dev_raw[slot].copy_(self.host_raw[slot], non_blocking=True)
+        base = self.dev_raw[slot].data_ptr()
         a = _lib.AddArgsT()
         a.rb = self.rb_desc()
         a.n = n
-        a.terminal_in = at("terminal")
-        a.reward_in = at("reward")
-        a.priority_in = at("priority") if self.prioritized else None
+        a.terminal_in = base + self._layout["terminal"][0]
+        a.reward_in = base + self._layout["reward"][0]
+        a.priority_in = base + self._layout["priority"][0] if self.prioritized else None
         for j, k in enumerate(self._keys):
             md = self.rb._key_to_replay_elem[k].metadata
-            a.rows[j].src = at(k)
+            a.rows[j].src = base + self._layout[k][0]
             a.rows[j].dst = self.rb._store[k].data_ptr()
             a.rows[j].row_bytes = md.row_bytes
             a.rows[j].which = 0
@@ -115,26 +123,26 @@ class DeviceReplay:
         self.rb._valid_index_stale = True
 
     @property
-    def h2d_bytes_per_row(self) -> int:
-        return sum(t[0].numel() * t.element_size() if t.dim() > 1 else t.element_size()
-                   for t in self.host.values())
+    def h2d_bytes_per_add(self) -> int:
+        """Bytes of the single host->device copy of one add launch (one staging block)."""
+        return self.block_bytes
 
     def add(self, **transition):
         """ReplayBuffer.add (one transition) on the device."""
-        self.stage(0, **transition)
+        self.stage(0, 0, **transition)
         self.launch_add(1)
 
     def add_rows(self, **arrays):
         """n consecutive add() calls from arrays with a leading dimension n."""
         n = len(arrays["terminal"])
-        if n > self.stage_rows:
-            self._alloc_stage(min(MAX_ADD, max(n, self.stage_rows)))
+        if n > self.stage_rows and self.stage_rows < MAX_ADD:
+            self._alloc_stage(min(MAX_ADD, n), self.stage_slots)
         for s0 in range(0, n, self.stage_rows):
             m = min(self.stage_rows, n - s0)
             for k, v in arrays.items():
-                self.host[k][:m] = torch.as_tensor(np.asarray(v)[s0:s0 + m]).to(self.host[k].dtype)
+                self.host_np[0][k][:m] = np.asarray(v)[s0:s0 + m]
             self.launch_add(m)
-            torch.cuda.current_stream().synchronize()  # the pinned rows are reused
+            torch.cuda.current_stream().synchronize()  # the pinned block is reused
 
     # ---- priorities ----------------------------------------------------------------
     def set_priority(self, indices, priorities):

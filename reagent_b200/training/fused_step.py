@@ -74,13 +74,15 @@ class FusedDqnStep:
 
             if not self.prioritized:
                 raise NotImplementedError("rng='device' covers the prioritized buffer")
-            self.dr = getattr(replay_buffer, "_device_resident", None) or DeviceReplay(replay_buffer, stage_rows=2)
-            if self.dr.stage_rows < 2:
-                self.dr._alloc_stage(2)
+            self.dr = getattr(replay_buffer, "_device_resident", None) or DeviceReplay(
+                replay_buffer, stage_rows=1, stage_slots=2)
+            if self.dr.stage_slots < 2:
+                self.dr._alloc_stage(self.dr.stage_rows, 2)
             self._idx_buf = [torch.zeros(self.B_global, dtype=torch.int64, device=self.dev)
                              for _ in range(2)]
             self._status_host = torch.zeros(2, dtype=torch.int32).pin_memory()
-            self.h2d_bytes = self.dr.h2d_bytes_per_row if self.online else 0
+            self._status_np = self._status_host.numpy()
+            self.h2d_bytes = self.dr.h2d_bytes_per_add if self.online else 0
             self.d2h_bytes = 4 + 8
         # warm-up outside capture (lazy allocations, cudaFuncSetAttribute, optimizer state)
         self._one_update(None)
@@ -159,7 +161,7 @@ class FusedDqnStep:
         """Device-resident draw: (optionally insert the staged transition,) select the global
         indices with the device MT19937 stream, gather this rank's rows."""
         if add:
-            self.dr.launch_add(1, row0=stage_row)
+            self.dr.launch_add(1, slot=stage_row)
         idx = self.dr.draw_indices(self.B_global, out=self._idx_buf[slot])
         return self.rb.sample_discrete_dqn_batch(self.B, self.A,
                                                  indices=idx[self.row0:self.row0 + self.B])
@@ -194,7 +196,7 @@ class FusedDqnStep:
                 loss = self._prefetch_update(i, marker)
             else:
                 if self.online:
-                    self.dr.launch_add(1, row0=i)
+                    self.dr.launch_add(1, slot=i)
                 loss = self.trainer.train_batch(self._device_sample(0, False), process_group=self.pg)
             loss_host.copy_(loss.reshape(1), non_blocking=True)
             self._status_host.copy_(self.dr.status, non_blocking=True)
@@ -226,14 +228,14 @@ class FusedDqnStep:
         if s["used"]:
             s["done"].synchronize()
         if self.dr is not None:
-            if self._status_host[0] != 0:  # sticky device status of an earlier step
+            if self._status_np[0] != 0:  # sticky device status of an earlier step
                 self.dr.raise_if_failed(self._status_host)
             if self.online:
                 if transition is None:
                     raise ValueError("online FusedDqnStep.step() needs the new transition")
                 # every slot's graph copies from its own pinned staging row; the slot's previous
                 # replay (and with it that H2D copy) was waited for above
-                self.dr.stage((self.k - 1) % len(self.slots), **transition)
+                self.dr.stage(0, (self.k - 1) % len(self.slots), **transition)
             s["graph"].replay()
             s["done"].record()
             s["used"] = True

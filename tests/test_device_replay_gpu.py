@@ -83,6 +83,7 @@ def test_device_add_and_draw_match_reference(name):
     # back to the host API: identical state to a buffer built entirely on the host
     dr.sync_to_host()
     host = _build(arrays, meta)
+    host._flush()  # staged host rows -> device storage
     assert int(rb.add_count) == int(host.add_count) and rb.size == host.size
     assert np.array_equal(rb._is_index_valid.numpy(), host._is_index_valid.numpy())
     assert np.array_equal(rb.sum_tree.heap, host.sum_tree.heap)
@@ -110,8 +111,9 @@ def test_device_set_priority_equals_sequential_host_sets():
     from reagent_b200 import _lib
 
     mx = np.array([rb.sum_tree.max_recorded_priority])
+    idx64 = np.ascontiguousarray(idx, dtype=np.int64)  # kept alive across the C call
     _lib.lib().rb200_sumtree_set_host(host_heap.ctypes.data, rb.sum_tree.depth,
-                                      idx.astype(np.int64).ctypes.data, val.ctypes.data, len(idx),
+                                      idx64.ctypes.data, val.ctypes.data, len(idx),
                                       mx.ctypes.data)
     dr.set_priority(idx, val)
     dr.raise_if_failed()
@@ -176,7 +178,7 @@ def test_online_fused_step_equals_host_loop():
     random.seed(77)
     from reagent_b200.replay_memory.device_replay import DeviceReplay
 
-    dr = DeviceReplay(rb_d2, stage_rows=2)
+    dr = DeviceReplay(rb_d2)
     losses_d, idx_d = [], []
     for i in range(12):
         dr.add(**{k: v[i] for k, v in extra.items()})

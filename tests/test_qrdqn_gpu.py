@@ -102,7 +102,7 @@ def test_dueling_quantile_forward_matches_reference():
     qo = G.oracle_net(arrays, "q0", meta["acts"] + ["linear"])
     want = O.mlp(qo, torch.from_numpy(arrays["batch.state"]))
     assert G.rel_err(out.reshape(B, -1), want) < TOL
-    assert isinstance(DiscreteQRDQN().net_builder, DuelingQuantile)
+    assert isinstance(DiscreteQRDQN(actions=["0", "1"]).net_builder, DuelingQuantile)
 
 
 def _qrdqn_oracle_chunked(qo, qt, b, *, gamma, num_atoms, chunk=256):
