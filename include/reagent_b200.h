@@ -194,6 +194,38 @@ int rb200_dqn_td_step_tc(const rb200_mlp_t* q_net, const rb200_mlp_t* q_target,
                          int64_t pack_ws_bytes, int32_t weights_packed, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* CPE heads of the DQN step: DQNTrainerBaseLightning._calculate_cpes           */
+/* (reagent/training/dqn_trainer_base.py:332-452), masked_softmax                 */
+/* (reagent/core/torch_utils.py:62-73).  The reward network and the CPE q-network  */
+/* are plain MLPs (rb200_mlp_forward / rb200_mlp_backward / rb200_mlp_wgrad); this  */
+/* entry computes both losses and d loss / d output of both networks.              */
+/* loss[0] = reward loss, loss[1] = CPE q-value loss.                               */
+/* ------------------------------------------------------------------------- */
+typedef struct rb200_cpe_args {
+  int32_t batch, num_actions, num_metrics;   /* B, A, M = len(metrics_to_score) */
+  const float* next_scores;        /* [B,A] q_network(next_state) (detached) */
+  const float* mask;               /* [B,A] possible_next_actions_mask (maxq) | next_action, or NULL */
+  float temperature;               /* rl.temperature */
+  const float* action;             /* [B,A] logged action (argmax = index) */
+  const float* metrics_reward;     /* [B,M] cat(reward, extras.metrics) */
+  const float* discount_src;       /* [B] or NULL */
+  float gamma;
+  int32_t discount_mode;           /* RB200_DISCOUNT_* */
+  const float* not_terminal;       /* [B] */
+  const float* reward_est;         /* [B, M*A] reward_network(state) */
+  const float* qcpe;               /* [B, M*A] q_network_cpe(state) */
+  const float* qcpe_target_next;   /* [B, M*A] q_network_cpe_target(next_state) */
+  int32_t loss_kind;               /* RB200_LOSS_* (rl.q_network_loss) for the CPE q-network */
+  float* dz_reward;                /* [B, M*A] */
+  float* dz_qcpe;                  /* [B, M*A] */
+  float* propensities_next;        /* [B,A] or NULL */
+  float* loss_partials;            /* [2 * ceil(B/256)] */
+  float* loss;                     /* [2] */
+  uint32_t* tile_counter;          /* [1] zero-initialised, self-resetting */
+} rb200_cpe_args_t;
+int rb200_cpe_heads(const rb200_cpe_args_t* args, void* stream);
+
+/* ------------------------------------------------------------------------- */
 /* QR-DQN (reagent/training/qrdqn_trainer.py:108-194).  The [hidden -> A*N] head  */
 /* is too wide for a row tile, so it runs as 2-D tiled launches:                   */
 /*   rb200_linear_forward      out = act(in . W^T + b), any N     (nn.Linear fwd) */

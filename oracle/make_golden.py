@@ -63,7 +63,7 @@ def _dump_net(arrays, prefix, module):
 def dqn_case(name, *, B=48, S=12, A=5, sizes=(24, 20), acts=("relu", "relu"), loss="huber",
              double_q=True, maxq=True, multi_steps=None, time_diff=False, boost=None,
              random_masks=False, gamma=0.97, tau=0.05, lr=1e-2, seed=0, dueling=False,
-             n_updates=None):
+             n_updates=None, cpe_metrics=None, temperature=0.01):
     n_updates = N_UPDATES if n_updates is None else n_updates
     rlt = ref("reagent.core.types")
     params = ref("reagent.core.parameters")
@@ -89,11 +89,27 @@ def dqn_case(name, *, B=48, S=12, A=5, sizes=(24, 20), acts=("relu", "relu"), lo
     rl = params.RLParameters(gamma=gamma, target_update_rate=tau, q_network_loss=loss,
                              maxq_learning=maxq, multi_steps=multi_steps,
                              use_seq_num_diff_as_time_diff=time_diff,
-                             reward_boost=boost)
+                             reward_boost=boost, temperature=temperature)
+    cpe = cpe_metrics is not None
+    reward_net = qcpe = qcpe_t = None
+    if cpe:  # CPE heads: reward network + q_network_cpe (+ target), dqn_trainer_base.py:243-452
+        n_out = (len(cpe_metrics) + 1) * A
+        reward_net = dqn_mod.FullyConnectedDQN(S, n_out, list(sizes), list(acts))
+        qcpe = dqn_mod.FullyConnectedDQN(S, n_out, list(sizes), list(acts))
+        with torch.no_grad():
+            for net in (reward_net, qcpe):
+                for _, b in _fc_params(net):
+                    b.normal_(0, 0.1)
+        qcpe_t = qcpe.get_target_network()
+        with torch.no_grad():
+            for w, b in _fc_params(qcpe_t):
+                w.add_(torch.randn_like(w) * 0.05)
+                b.add_(torch.randn_like(b) * 0.05)
     trainer = tr.DQNTrainer(
-        q, qt, None, actions=actions, rl=rl, double_q_learning=double_q, minibatch_size=B,
+        q, qt, reward_net, qcpe, qcpe_t, metrics_to_score=list(cpe_metrics) if cpe else None,
+        actions=actions, rl=rl, double_q_learning=double_q, minibatch_size=B,
         optimizer=union.Optimizer__Union(Adam=union.classes["Adam"](lr=lr)),
-        evaluation=params.EvaluationParameters(calc_cpe_in_training=False))
+        evaluation=params.EvaluationParameters(calc_cpe_in_training=cpe))
     act_idx = torch.randint(A, (B,))
     nact_idx = torch.randint(A, (B,))
     not_terminal = (torch.rand(B, 1) > 0.2).float()
@@ -108,6 +124,8 @@ def dqn_case(name, *, B=48, S=12, A=5, sizes=(24, 20), acts=("relu", "relu"), lo
         action=torch.nn.functional.one_hot(act_idx, A).float(),
         next_action=torch.nn.functional.one_hot(nact_idx, A).float() * not_terminal,
         possible_actions_mask=torch.ones(B, A), possible_next_actions_mask=pnam)
+    if cpe:
+        batch["metrics"] = torch.randn(B, len(cpe_metrics))
     rbatch = rlt.DiscreteDqnInput(
         state=rlt.FeatureData(batch["state"]), next_state=rlt.FeatureData(batch["next_state"]),
         reward=batch["reward"], time_diff=batch["time_diff"],
@@ -115,26 +133,45 @@ def dqn_case(name, *, B=48, S=12, A=5, sizes=(24, 20), acts=("relu", "relu"), lo
         not_terminal=batch["not_terminal"], action=batch["action"],
         next_action=batch["next_action"], possible_actions_mask=batch["possible_actions_mask"],
         possible_next_actions_mask=batch["possible_next_actions_mask"],
-        extras=rlt.ExtraData(action_probability=torch.ones(B, 1)))
+        extras=rlt.ExtraData(action_probability=torch.ones(B, 1),
+                             metrics=batch.get("metrics")))
     arrays = {f"batch.{k}": _np(v) for k, v in batch.items()}
     _dump_net(arrays, "q0", q)
     _dump_net(arrays, "qt0", qt)
+    if cpe:
+        _dump_net(arrays, "r0", reward_net)
+        _dump_net(arrays, "c0", qcpe)
+        _dump_net(arrays, "ct0", qcpe_t)
     opts = [o["optimizer"] for o in trainer.configure_optimizers()]
-    losses = []
+    assert len(opts) == (4 if cpe else 2)
+    losses, cpe_losses = [], []
     for it in range(n_updates):
         cap = {}
         out = run_update(trainer, rbatch, it, opts, capture=cap)
         losses.append(out[0])
+        if cpe:
+            cpe_losses.append([out[1], out[2]])
         if it == 0:
             for i, g in enumerate(cap[0]):
                 arrays[f"grad0.{i}"] = _np(g)
             arrays["all_q0"] = _np(trainer.all_action_scores)
+            if cpe:
+                for i, g in enumerate(cap[1]):
+                    arrays[f"grad0r.{i}"] = _np(g)
+                for i, g in enumerate(cap[2]):
+                    arrays[f"grad0c.{i}"] = _np(g)
     arrays["losses"] = np.array(losses, dtype=np.float64)
     _dump_net(arrays, "qN", q)
     _dump_net(arrays, "qtN", qt)
+    if cpe:
+        arrays["cpe_losses"] = np.array(cpe_losses, dtype=np.float64)
+        _dump_net(arrays, "rN", reward_net)
+        _dump_net(arrays, "cN", qcpe)
+        _dump_net(arrays, "ctN", qcpe_t)
     meta = dict(kind="dqn", B=B, S=S, A=A, sizes=list(sizes), acts=list(acts), loss=loss,
                 double_q=double_q, maxq=maxq, multi_steps=multi_steps, time_diff=time_diff,
-                boost=boost, gamma=gamma, tau=tau, lr=lr, n_updates=n_updates, dueling=dueling)
+                boost=boost, gamma=gamma, tau=tau, lr=lr, n_updates=n_updates, dueling=dueling,
+                cpe_metrics=cpe_metrics, temperature=temperature)
     _save(name, arrays, meta)
 
 
@@ -180,6 +217,8 @@ def qrdqn_case(name, *, B=32, S=9, A=4, N=7, sizes=(20, 12), acts=("relu", "relu
         action=torch.nn.functional.one_hot(act_idx, A).float(),
         next_action=torch.nn.functional.one_hot(nact_idx, A).float() * not_terminal,
         possible_actions_mask=torch.ones(B, A), possible_next_actions_mask=pnam)
+    if cpe:
+        batch["metrics"] = torch.randn(B, len(cpe_metrics))
     rbatch = rlt.DiscreteDqnInput(
         state=rlt.FeatureData(batch["state"]), next_state=rlt.FeatureData(batch["next_state"]),
         reward=batch["reward"], time_diff=batch["time_diff"],
@@ -751,6 +790,10 @@ def main(only=None):
     add(dqn_case, "dqn_dueling_double", dueling=True, sizes=(24, 16), seed=6)
     add(dqn_case, "dqn_dueling_mse_masked", dueling=True, sizes=(16,), acts=("tanh",), loss="mse",
         double_q=False, random_masks=True, B=37, S=7, A=3, seed=7)
+    # CPE heads (calc_cpe_in_training=True, the reference default): reward + q_network_cpe
+    add(dqn_case, "dqn_cpe_huber", cpe_metrics=["m1"], seed=8, random_masks=True, temperature=0.5)
+    add(dqn_case, "dqn_cpe_mse_sarsa_multistep", cpe_metrics=[], loss="mse", maxq=False,
+        multi_steps=3, seed=9, B=37, S=7, A=3, sizes=(10, 6), temperature=1.0)
     add(replay_case, "replay_uniform_h1", prioritized=False, cap=100, n_add=73, B=16)
     add(replay_case, "replay_uniform_h3_wrap", prioritized=False, cap=64, n_add=150, B=32, horizon=3, seed=1, with_extra=True)
     add(replay_case, "replay_uniform_h5_cont", prioritized=False, cap=128, n_add=300, B=24, horizon=5, seed=2, continuous=True, gamma=0.97)

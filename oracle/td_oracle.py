@@ -171,6 +171,63 @@ def dqn_update(q: Net, qt: Net, adam: AdamState, batch, *, gamma, tau, **kw):
     return float(loss.detach()), grads, aux
 
 
+def masked_softmax(x, mask, temperature):
+    """reagent/core/torch_utils.py:62-73"""
+    x = x / temperature
+    mmx = x - ((1.0 - mask) * 1e20)
+    mmx = mmx - torch.max(mmx, dim=1, keepdim=True)[0]
+    e = torch.exp(mmx) * mask
+    out = e / e.sum(dim=1, keepdim=True)
+    out[out != out] = 0
+    return out
+
+
+def dqn_cpe_losses(q: Net, reward_net: Net, qcpe: Net, qcpe_t: Net, batch, *, gamma, temperature,
+                   num_actions, maxq=True, loss="mse", discount_src=None):
+    """_calculate_cpes (reagent/training/dqn_trainer_base.py:332-452): (reward loss, CPE
+    q-value loss).  `batch["metrics"]` (B, M-1) are the extra metrics, may be absent."""
+    A = num_actions
+    mrc = batch["reward"]
+    if batch.get("metrics") is not None and batch["metrics"].shape[1] > 0:
+        mrc = torch.cat((batch["reward"], batch["metrics"]), dim=1)
+    M = mrc.shape[1]
+    offsets = torch.arange(0, M * A, A, dtype=torch.long)
+    logged = torch.argmax(batch["action"], dim=1, keepdim=True)
+    with torch.no_grad():
+        next_scores = mlp(q, batch["next_state"])  # dqn_trainer.py:268 (after the q step)
+    mask = (batch["possible_next_actions_mask"] if maxq else batch["next_action"]).float()
+    prop = masked_softmax(next_scores, mask, temperature)
+    discount = torch.full_like(batch["reward"], gamma)
+    if discount_src is not None:
+        discount = torch.pow(gamma, discount_src.float())
+    not_done = batch["not_terminal"].float()
+    r_est = mlp(reward_net, batch["state"]).gather(1, offsets + logged)
+    reward_loss = F.mse_loss(r_est, mrc)
+    metric_q = mlp(qcpe, batch["state"]).gather(1, offsets + logged)
+    chunks = torch.chunk(mlp(qcpe_t, batch["next_state"]).detach(), M, dim=1)
+    tgt = []
+    for i, per_metric in enumerate(chunks):
+        nq = torch.sum(per_metric * prop, 1, keepdim=True) * not_done
+        tgt.append(mrc[:, i:i + 1] + discount * nq)
+    tgt = torch.cat(tgt, dim=1)
+    fn = F.mse_loss if loss == "mse" else F.smooth_l1_loss
+    return reward_loss, fn(metric_q, tgt), prop
+
+
+def dqn_cpe_update(q, reward_net, adam_r, qcpe, qcpe_t, adam_c, batch, *, tau, **kw):
+    """The two CPE optimizer steps of one DQNTrainer update and the soft update of the CPE
+    target; call AFTER dqn_update's Adam step of q (dqn_trainer.py:256-304).  Returns
+    (reward_loss, cpe_loss, reward grads, cpe grads)."""
+    pr, pc = net_params(reward_net), net_params(qcpe)
+    rl, cl, _ = dqn_cpe_losses(q, reward_net, qcpe, qcpe_t, batch, **kw)
+    gr = [g.detach().clone() for g in torch.autograd.grad(rl, pr)]
+    adam_r.step(pr, gr)
+    gc = [g.detach().clone() for g in torch.autograd.grad(cl, pc)]
+    adam_c.step(pc, gc)
+    soft_update(qcpe_t, qcpe, tau)
+    return float(rl.detach()), float(cl.detach()), gr, gc
+
+
 # ---------------------------------------------------------------------------
 # Gaussian actor head (reagent/models/actor.py:169-261)
 # ---------------------------------------------------------------------------

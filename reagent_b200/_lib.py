@@ -155,6 +155,16 @@ class SampleArgsT(C.Structure):
     ]
 
 
+class CpeArgsT(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("num_actions", C.c_int32), ("num_metrics", C.c_int32),
+                ("next_scores", _vp), ("mask", _vp), ("temperature", C.c_float), ("action", _vp),
+                ("metrics_reward", _vp), ("discount_src", _vp), ("gamma", C.c_float),
+                ("discount_mode", C.c_int32), ("not_terminal", _vp), ("reward_est", _vp),
+                ("qcpe", _vp), ("qcpe_target_next", _vp), ("loss_kind", C.c_int32),
+                ("dz_reward", _vp), ("dz_qcpe", _vp), ("propensities_next", _vp),
+                ("loss_partials", _vp), ("loss", _vp), ("tile_counter", _vp)]
+
+
 class ReplayDevT(C.Structure):
     _fields_ = [("state", _vp), ("capacity", C.c_int32), ("update_horizon", C.c_int32),
                 ("valid", _vp), ("terminal", _vp), ("reward", _vp), ("tree", _vp),
@@ -251,6 +261,7 @@ def _declare(lib):
     lib.rb200_grad_reduce.argtypes = [_vp, C.c_int32, C.c_int64, _vp, _vp]
     lib.rb200_adam_soft_update.argtypes = [C.POINTER(AdamArgsT), _vp]
     lib.rb200_soft_update.argtypes = [_vp, _vp, C.c_int64, C.c_float, C.c_float, _vp]
+    lib.rb200_cpe_heads.argtypes = [C.POINTER(CpeArgsT), _vp]
     lib.rb200_replay_add_device.argtypes = [C.POINTER(AddArgsT), _vp]
     lib.rb200_sumtree_set_device.argtypes = [_vp, C.c_int32, _vp, _vp, C.c_int32, _vp, _vp, _vp]
     lib.rb200_per_draw_indices.argtypes = [C.POINTER(PerDrawArgsT), _vp]

@@ -52,17 +52,31 @@ class DiscreteDQN(_DiscretePolicyMixin):
     optimizer: Optimizer__Union = field(default_factory=Optimizer__Union.default)
     # reagent/model_managers/discrete/discrete_dqn.py:33-36: the reference defaults to Dueling
     net_builder: Union[Dueling, FullyConnected] = field(default_factory=Dueling)
-    eval_parameters: EvaluationParameters = field(
-        default_factory=lambda: EvaluationParameters(calc_cpe_in_training=False))
+    # :37-42: the reward / CPE networks are plain FullyConnected
+    cpe_net_builder: Union[Dueling, FullyConnected] = field(default_factory=FullyConnected)
+    # EvaluationParameters() has calc_cpe_in_training=True, as in the reference
+    # (reagent/core/parameters.py:118-120)
+    eval_parameters: EvaluationParameters = field(default_factory=EvaluationParameters)
+    metrics_to_score: Optional[List[str]] = None
 
     def build_trainer(self, normalization_data_map: Dict[str, NormalizationData], use_gpu: bool,
                       reward_options=None) -> DQNTrainer:
+        """discrete_dqn.py:73-116"""
         dev = _device(use_gpu)
-        q_network = self.net_builder.build_q_network(
-            None, normalization_data_map[NormalizationKey.STATE], len(self.actions)).to(dev)
+        s_norm = normalization_data_map[NormalizationKey.STATE]
+        q_network = self.net_builder.build_q_network(None, s_norm, len(self.actions)).to(dev)
         q_network_target = q_network.get_target_network()
+        reward_network = q_network_cpe = q_network_cpe_target = None
+        metrics = list(self.metrics_to_score or [])
+        if self.eval_parameters.calc_cpe_in_training:
+            n_out = (len(metrics) + 1) * len(self.actions)  # metrics + reward
+            reward_network = self.cpe_net_builder.build_q_network(None, s_norm, n_out).to(dev)
+            q_network_cpe = self.cpe_net_builder.build_q_network(None, s_norm, n_out).to(dev)
+            q_network_cpe_target = q_network_cpe.get_target_network()
         return DQNTrainer(
-            q_network=q_network, q_network_target=q_network_target, reward_network=None,
+            q_network=q_network, q_network_target=q_network_target,
+            reward_network=reward_network, q_network_cpe=q_network_cpe,
+            q_network_cpe_target=q_network_cpe_target, metrics_to_score=metrics,
             actions=self.actions, rl=self.rl, double_q_learning=self.double_q_learning,
             minibatch_size=self.minibatch_size, optimizer=self.optimizer,
             evaluation=self.eval_parameters).to(dev)

@@ -77,12 +77,18 @@ class DQNTrainer(DQNTrainerBaseLightning):
 
     # ------------------------------------------------------------------
     def configure_optimizers(self):
-        """[Adam(q_network), SoftUpdate(target <- q_network)] (dqn_trainer.py:119-155)."""
+        """[Adam(q_network), (Adam(reward_network), Adam(q_network_cpe) with CPE,)
+        SoftUpdate(targets <- sources)] (dqn_trainer.py:119-155)."""
         optimizers = []
         target_params = list(self.q_network_target.parameters())
         source_params = list(self.q_network.parameters())
         optimizers.append(
             self.q_network_optimizer.make_optimizer_scheduler(self.q_network.parameters()))
+        if self.calc_cpe_in_training:
+            cpe_targets, cpe_sources, cpe_optimizers = self._configure_cpe_optimizers()
+            target_params += cpe_targets
+            source_params += cpe_sources
+            optimizers += cpe_optimizers
         optimizers.append(
             SoftUpdate.make_optimizer_scheduler(target_params, source_params, tau=self.tau))
         return optimizers
@@ -251,11 +257,18 @@ class DQNTrainer(DQNTrainerBaseLightning):
 
     # ------------------------------------------------------------------
     def train_step_gen(self, training_batch: rlt.DiscreteDqnInput, batch_idx: int):
-        """Yields (td_loss, soft_update_loss) -- dqn_trainer.py:241-304 with CPE off."""
+        """Yields (td_loss, [reward_loss, cpe_metric_loss,] soft_update_loss) --
+        dqn_trainer.py:241-304."""
         self._check_input(training_batch)
         td_loss = self._td_step(training_batch)
         yield self.fused_loss(td_loss)
         td_loss = td_loss.detach()
+        if self.calc_cpe_in_training:
+            # evaluated here, after the q-network's optimizer step, like the reference's
+            # generator (dqn_trainer.py:266-279)
+            cpe = self._calculate_cpes(training_batch)
+            yield self.fused_loss(cpe[0])
+            yield self.fused_loss(cpe[1])
         if self.has_real_reporter or self.logger:
             self._log_dqn(td_loss, training_batch)
         yield self.soft_update_result()
@@ -277,6 +290,12 @@ class DQNTrainer(DQNTrainerBaseLightning):
                                target=self.q_network_target.arena, tau=self.tau, tc_pack=tcp)
         if packed:
             self._tc_images_state = self._tc_state()
+        if self.calc_cpe_in_training:
+            cpe = self._calculate_cpes(training_batch)
+            dp_fused_step(opts[1], self.reward_network.arena, process_group)
+            dp_fused_step(opts[2], self.q_network_cpe.arena, process_group,
+                          target=self.q_network_cpe_target.arena, tau=self.tau)
+            self.cpe_losses = cpe
         self.all_batches_processed += 1
         return self._ws["loss"]
 

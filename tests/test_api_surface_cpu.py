@@ -36,8 +36,12 @@ def test_trainer_constructors_and_optimizer_order():
     t = DQNTrainer(q, q.get_target_network(), actions=["a", "b", "c"], evaluation=ev)
     assert [type(o) for o in t.optimizers()] == [FusedAdam, SoftUpdate]
     assert inspect.signature(t.train_step_gen).parameters["training_batch"].annotation is rlt.DiscreteDqnInput
-    with pytest.raises(NotImplementedError):
-        DQNTrainer(q, q.get_target_network(), actions=["a", "b", "c"])  # CPE on by default
+    with pytest.raises(AssertionError, match="reward_network is required for CPE"):
+        DQNTrainer(q, q.get_target_network(), actions=["a", "b", "c"])  # CPE on by default (as the reference)
+    rn, qc = FullyConnectedDQN(8, 3, [16], ["relu"]), FullyConnectedDQN(8, 3, [16], ["relu"])
+    tc = DQNTrainer(q, q.get_target_network(), rn, qc, qc.get_target_network(), actions=["a", "b", "c"])
+    assert [type(o) for o in tc.optimizers()] == [FusedAdam, FusedAdam, FusedAdam, SoftUpdate]
+    assert tc.metrics_to_score == ["reward"] and tc.reward_idx_offsets.tolist() == [0]
     qq = FullyConnectedDQN(8, 3, [16], ["relu"], num_atoms=5)
     tq = QRDQNTrainer(qq, qq.get_target_network(), actions=["a", "b", "c"], num_atoms=5, evaluation=ev)
     assert tq.quantiles.shape == (1, 5) and abs(float(tq.quantiles[0, 0]) - 0.1) < 1e-7
@@ -97,8 +101,10 @@ def test_net_builders_and_managers_construct():
     assert ParametricFullyConnected().build_q_network(s, a).fc.layers == [8, 128, 64, 1]
     assert GaussianFullyConnected().build_actor(None, s, a).fc.layers == [6, 128, 64, 4]
     from reagent_b200.model_managers import DiscreteDQN
+    m = DiscreteDQN(actions=["0", "1"])
+    assert m.eval_parameters.calc_cpe_in_training  # the reference default (core/parameters.py:118-120)
     with pytest.raises(RuntimeError):
-        DiscreteDQN(actions=["0", "1"]).build_trainer({"state": s}, use_gpu=False)
+        m.build_trainer({"state": s}, use_gpu=False)
 
 
 def test_input_makers_match_reference_formulas():
@@ -164,7 +170,7 @@ def test_ctypes_mirrors_match_the_library_struct_sizes():
                "rb200_feature_col_t": _lib.FeatureColT, "rb200_dqn_args_t": _lib.DqnArgsT,
                "rb200_qrdqn_args_t": _lib.QrdqnArgsT, "rb200_ac_args_t": _lib.AcArgsT,
                "rb200_adam_args_t": _lib.AdamArgsT, "rb200_gather_spec_t": _lib.GatherSpecT,
-               "rb200_sample_args_t": _lib.SampleArgsT, "rb200_replay_dev_t": _lib.ReplayDevT,
+               "rb200_sample_args_t": _lib.SampleArgsT, "rb200_replay_dev_t": _lib.ReplayDevT, "rb200_cpe_args_t": _lib.CpeArgsT,
                "rb200_add_args_t": _lib.AddArgsT, "rb200_per_draw_args_t": _lib.PerDrawArgsT}
     lib = _lib.lib()
     for name, mirror in mirrors.items():

@@ -455,3 +455,89 @@ def test_dqn_config0_matches_reference(path, monkeypatch):
                 assert float(d.max()) <= 2.0 * meta["lr"] * 1.01, (prefix, i)
                 frac = float((d > TOL * float(np.abs(ref).max())).double().mean())
                 assert frac < 0.01, (prefix, i, frac)
+
+
+# ---------------------------------------------------------------------------
+# CPE heads (calc_cpe_in_training=True, the reference default): dqn_trainer_base.py:243-452
+# ---------------------------------------------------------------------------
+CPE_CASES = ["dqn_cpe_huber", "dqn_cpe_mse_sarsa_multistep"]
+
+
+def _build_cpe_trainer(meta, arrays):
+    from reagent_b200.core.parameters import EvaluationParameters, RLParameters
+    from reagent_b200.models import FullyConnectedDQN
+    from reagent_b200.optimizer import Optimizer__Union
+    from reagent_b200.training import DQNTrainer
+
+    S, A = meta["S"], meta["A"]
+    n_out = (len(meta["cpe_metrics"]) + 1) * A
+    q = FullyConnectedDQN(S, A, meta["sizes"], meta["acts"])
+    qt = q.get_target_network()
+    rn = FullyConnectedDQN(S, n_out, meta["sizes"], meta["acts"])
+    qc = FullyConnectedDQN(S, n_out, meta["sizes"], meta["acts"])
+    qct = qc.get_target_network()
+    for net, prefix in ((q, "q0"), (qt, "qt0"), (rn, "r0"), (qc, "c0"), (qct, "ct0")):
+        G.load_into_module(arrays, prefix, net)
+    rl = RLParameters(gamma=meta["gamma"], target_update_rate=meta["tau"],
+                      q_network_loss=meta["loss"], maxq_learning=meta["maxq"],
+                      multi_steps=meta["multi_steps"], temperature=meta["temperature"],
+                      use_seq_num_diff_as_time_diff=meta["time_diff"], reward_boost=meta["boost"])
+    t = DQNTrainer(q.cuda(), qt.cuda(), rn.cuda(), qc.cuda(), qct.cuda(),
+                   metrics_to_score=list(meta["cpe_metrics"]),
+                   actions=[str(i) for i in range(A)], rl=rl, double_q_learning=meta["double_q"],
+                   minibatch_size=meta["B"], optimizer=Optimizer__Union.default(lr=meta["lr"]),
+                   evaluation=EvaluationParameters(calc_cpe_in_training=True))
+    return t.cuda()
+
+
+@pytest.mark.parametrize("fast", [False, True])
+@pytest.mark.parametrize("name", CPE_CASES)
+def test_dqn_cpe_matches_reference(name, fast):
+    from reagent_b200.core import types as rlt
+    from reagent_b200.training import run_update
+    from reagent_b200.training.workspace import param_grads
+
+    arrays, meta = G.load(name)
+    t = _build_cpe_trainer(meta, arrays)
+    assert len(t.configure_optimizers()) == 4
+    b = G.batch_tensors(arrays, "cuda")
+    batch = _rlt_batch(b, meta)
+    batch.extras = rlt.ExtraData(action_probability=torch.ones_like(b["reward"]),
+                                 metrics=b.get("metrics"))
+    for it in range(meta["n_updates"]):
+        if fast:
+            td = float(t.train_batch(batch, it))
+            rl_, cl_ = (float(x) for x in t.cpe_losses)
+        else:
+            out = run_update(t, batch, it)
+            assert len(out) == 4
+            td, rl_, cl_ = float(out[0]), float(out[1]), float(out[2])
+        for got, want in ((td, arrays["losses"][it]), (rl_, arrays["cpe_losses"][it][0]),
+                          (cl_, arrays["cpe_losses"][it][1])):
+            assert abs(got - want) <= TOL * max(1.0, abs(want)), (it, got, want)
+    for net, prefix in ((t.q_network, "qN"), (t.q_network_target, "qtN"), (t.reward_network, "rN"),
+                        (t.q_network_cpe, "cN"), (t.q_network_cpe_target, "ctN")):
+        ps = list(net.parameters())
+        for i, (w, bb) in enumerate(G.net_pairs(arrays, prefix)):
+            assert G.rel_err(ps[2 * i], w) < TOL, (prefix, i)
+            assert G.rel_err(ps[2 * i + 1], bb) < TOL, (prefix, i)
+
+
+def test_dqn_cpe_gradients_match_reference():
+    from reagent_b200.core import types as rlt
+    from reagent_b200.training.workspace import param_grads
+
+    arrays, meta = G.load("dqn_cpe_huber")
+    t = _build_cpe_trainer(meta, arrays)
+    b = G.batch_tensors(arrays, "cuda")
+    batch = _rlt_batch(b, meta)
+    batch.extras = rlt.ExtraData(action_probability=torch.ones_like(b["reward"]), metrics=b.get("metrics"))
+    opts = t.optimizers()
+    l0 = t.training_step(batch, 0, 0)
+    opts[0].zero_grad(); l0.backward(); opts[0].step()
+    l1 = t.training_step(batch, 0, 1)  # reward loss: both CPE gradients exist from here on
+    for i, g in enumerate(param_grads(t.reward_network.arena, list(t.reward_network.parameters()))):
+        assert G.rel_err(g, arrays[f"grad0r.{i}"]) < TOL, f"reward grad {i}"
+    for i, g in enumerate(param_grads(t.q_network_cpe.arena, list(t.q_network_cpe.parameters()))):
+        assert G.rel_err(g, arrays[f"grad0c.{i}"]) < TOL, f"cpe grad {i}"
+    assert abs(float(l1) - arrays["cpe_losses"][0][0]) <= TOL * max(1.0, abs(arrays["cpe_losses"][0][0]))

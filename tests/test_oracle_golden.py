@@ -264,3 +264,43 @@ def test_replay_oracle_plus_inputmaker_formulas_match_reference(name):
             eye = np.eye(A, dtype=np.float32)
             assert np.array_equal(eye[ob["action"]], arrays[pre + "action"])
             assert np.array_equal(eye[ob["next_action"]] * (~term)[:, None], arrays[pre + "next_action"])
+
+
+DQN_CPE_CASES = ["dqn_cpe_huber", "dqn_cpe_mse_sarsa_multistep"]
+
+
+@pytest.mark.parametrize("name", DQN_CPE_CASES)
+def test_dqn_cpe_oracle_matches_reference(name):
+    """CPE heads (dqn_trainer_base.py:332-452): the oracle's reward / CPE q-value losses,
+    gradients and post-update networks against the unmodified reference DQNTrainer with
+    calc_cpe_in_training=True."""
+    arrays, meta = G.load(name)
+    acts = meta["acts"] + ["linear"]
+    q = G.oracle_net(arrays, "q0", acts, requires_grad=True)
+    qt = G.oracle_net(arrays, "qt0", acts)
+    rn = G.oracle_net(arrays, "r0", acts, requires_grad=True)
+    qc = G.oracle_net(arrays, "c0", acts, requires_grad=True)
+    qct = G.oracle_net(arrays, "ct0", acts)
+    batch = G.batch_tensors(arrays)
+    adam = O.AdamState(O.net_params(q), lr=meta["lr"])
+    adam_r = O.AdamState(O.net_params(rn), lr=meta["lr"])
+    adam_c = O.AdamState(O.net_params(qc), lr=meta["lr"])
+    kw = _dqn_kwargs(meta, batch)
+    ckw = dict(gamma=meta["gamma"], temperature=meta["temperature"], num_actions=meta["A"],
+               maxq=meta["maxq"], loss=meta["loss"], discount_src=kw.get("discount_src"))
+    for it in range(meta["n_updates"]):
+        loss, grads, aux = O.dqn_update(q, qt, adam, batch, gamma=meta["gamma"], tau=meta["tau"], **kw)
+        rl, cl, gr, gc = O.dqn_cpe_update(q, rn, adam_r, qc, qct, adam_c, batch, tau=meta["tau"], **ckw)
+        assert abs(loss - arrays["losses"][it]) <= 1e-6 * max(1.0, abs(arrays["losses"][it]))
+        for got, want in ((rl, arrays["cpe_losses"][it][0]), (cl, arrays["cpe_losses"][it][1])):
+            assert abs(got - want) <= 1e-6 * max(1.0, abs(want)), (it, got, want)
+        if it == 0:
+            for i, g in enumerate(gr):
+                assert G.rel_err(g, arrays[f"grad0r.{i}"]) < 1e-6
+            for i, g in enumerate(gc):
+                assert G.rel_err(g, arrays[f"grad0c.{i}"]) < 1e-6
+    for net, prefix in ((q, "qN"), (qt, "qtN"), (rn, "rN"), (qc, "cN"), (qct, "ctN")):
+        ps = O.net_params(net)
+        for i, (w, b) in enumerate(G.net_pairs(arrays, prefix)):
+            assert G.rel_err(ps[2 * i], w) < 1e-6, (prefix, i)
+            assert G.rel_err(ps[2 * i + 1], b) < 1e-6, (prefix, i)
