@@ -325,10 +325,15 @@ int rb200_ac_actor_step(const rb200_mlp_t* actor, const rb200_mlp_t* q1, const r
 /* ------------------------------------------------------------------------- */
 /* Weight gradients: dW_l = dZ_l^T . A_{l-1}, db_l = sum_b dZ_l, split over    */
 /* the batch; partial s lands at gpart + s*n_params (arena layout).            */
+/* tcgen05.mma kind::tf32 (3xTF32, MN-major operands staged from the row-major */
+/* activations, accumulator in Tensor Memory: rb200_wgrad_tc.cu); the mma.sync */
+/* kernel of rb200_optim.cu runs when RB200_DISABLE_TCGEN05 / RB200_WGRAD_TC=0. */
 /* Replaces autograd's Linear backward (torch) reached from                    */
 /* loss.backward() in the Lightning loop (reagent_lightning_module.py:108-133).*/
 /* ------------------------------------------------------------------------- */
 int rb200_wgrad_splits(int batch);
+/* slabs for this network (tcgen05 kernel: enough (tile, slab) jobs to fill the SMs twice) */
+int rb200_wgrad_splits_for(const rb200_mlp_t* net, int32_t batch);
 int rb200_mlp_wgrad(const rb200_mlp_t* net, const float* net_input, int32_t batch,
                     const rb200_net_ws_t* ws, float* gpart, int32_t splits, void* stream);
 /* g[i] = sum_s gpart[s*P + i]  (fixed order; feeds all-reduce / .grad views) */

@@ -256,6 +256,7 @@ def _declare(lib):
                                         C.POINTER(AcArgsT), C.POINTER(NetWsT), C.POINTER(NetWsT),
                                         C.POINTER(NetWsT), _vp]
     lib.rb200_wgrad_splits.argtypes = [C.c_int]
+    lib.rb200_wgrad_splits_for.argtypes = [C.POINTER(MlpT), C.c_int32]
     lib.rb200_mlp_wgrad.argtypes = [C.POINTER(MlpT), _vp, C.c_int32, C.POINTER(NetWsT), _vp,
                                     C.c_int32, _vp]
     lib.rb200_grad_reduce.argtypes = [_vp, C.c_int32, C.c_int64, _vp, _vp]

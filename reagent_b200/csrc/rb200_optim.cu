@@ -355,12 +355,36 @@ extern "C" int rb200_wgrad_splits(int batch) {
   return s;
 }
 
+int rb200_wgrad_tc_launch(const rb200_mlp_t* net, const float* net_input, int32_t batch,
+                          const rb200_net_ws_t* ws, float* gpart, int32_t splits, void* stream);
+
+static bool wgrad_use_tc() {
+  const char* d = getenv("RB200_DISABLE_TCGEN05");
+  const char* w = getenv("RB200_WGRAD_TC");
+  return !(d && d[0] && d[0] != '0') && !(w && w[0] == '0');
+}
+
+// Batch slabs for a network: enough (layer tile, slab) jobs to fill the 148 SMs about twice,
+// slabs of at least 128 rows (the tcgen05 kernel stages 32-row chunks; fewer, longer slabs
+// keep the partials the Adam kernel has to read small for wide heads).
+extern "C" int rb200_wgrad_splits_for(const rb200_mlp_t* net, int32_t batch) {
+  if (!net || !wgrad_use_tc()) return rb200_wgrad_splits(batch);
+  int jobs = 0;
+  for (int l = 0; l < net->n_layers; ++l) jobs += ceil_div(net->dims[l + 1], 128) * ceil_div(net->dims[l], 256);
+  int s = ceil_div(296, jobs < 1 ? 1 : jobs);
+  const int smax = batch / 128 < 1 ? 1 : batch / 128;
+  if (s > smax) s = smax;
+  if (s > 64) s = 64;
+  return s < 1 ? 1 : s;
+}
+
 extern "C" int rb200_mlp_wgrad(const rb200_mlp_t* net, const float* net_input, int32_t batch,
                                const rb200_net_ws_t* ws, float* gpart, int32_t splits,
                                void* stream) {
   if (!net || !ws || !gpart) { set_last_error("rb200_mlp_wgrad: null argument"); return RB200_E_INVALID; }
   if (int rc = validate_mlp(net, "net")) return rc;
   if (batch <= 0 || splits <= 0) { set_last_error("rb200_mlp_wgrad: bad batch/splits"); return RB200_E_INVALID; }
+  if (wgrad_use_tc()) return rb200_wgrad_tc_launch(net, net_input, batch, ws, gpart, splits, stream);
   WgradParams p = {};
   p.n_layers = net->n_layers;
   p.B = batch;

@@ -33,7 +33,7 @@ def ensure_gpart(arena: ParamArena, splits: int):
 
 def wgrad(arena: ParamArena, ws: NetWorkspace, net_input, batch: int):
     """Launch the split-K weight-gradient kernel for one network."""
-    splits = _lib.lib().rb200_wgrad_splits(batch)
+    splits = _lib.lib().rb200_wgrad_splits_for(arena.desc(), batch)
     g = ensure_gpart(arena, splits)
     rc = _lib.lib().rb200_mlp_wgrad(arena.desc(), _lib.ptr(net_input), batch, ws.c,
                                     g.data_ptr(), splits, _lib.cur_stream())
