@@ -325,9 +325,9 @@ int rb200_ac_actor_step(const rb200_mlp_t* actor, const rb200_mlp_t* q1, const r
 /* ------------------------------------------------------------------------- */
 /* Weight gradients: dW_l = dZ_l^T . A_{l-1}, db_l = sum_b dZ_l, split over    */
 /* the batch; partial s lands at gpart + s*n_params (arena layout).            */
-/* tcgen05.mma kind::tf32 (3xTF32, MN-major operands staged from the row-major */
-/* activations, accumulator in Tensor Memory: rb200_wgrad_tc.cu); the mma.sync */
-/* kernel of rb200_optim.cu runs when RB200_DISABLE_TCGEN05 / RB200_WGRAD_TC=0. */
+/* Default: mma.sync 3xTF32 tiles (rb200_optim.cu).  RB200_WGRAD_TC=1 selects the  */
+/* tcgen05 kernel (rb200_wgrad_tc.cu: operands transposed into K-major planes while */
+/* staging, accumulator in Tensor Memory); same results to 1e-5, same speed today.  */
 /* Replaces autograd's Linear backward (torch) reached from                    */
 /* loss.backward() in the Lightning loop (reagent_lightning_module.py:108-133).*/
 /* ------------------------------------------------------------------------- */

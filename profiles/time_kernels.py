@@ -44,6 +44,14 @@ print("sample  us", timeit(lambda i: rb.sample_discrete_dqn_batch(bench.B, bench
 print("td+wgrad us", timeit(lambda i: t._td_step(batches[i % 8])))
 print("td fwd only us", timeit(lambda i: t._td_step(batches[i % 8], do_backward=False)))
 ws = t._ws
-print("wgrad us", timeit(lambda i: wgrad(t.q_network.arena, ws["net"], batches[0].state.float_features, bench.B)))
+os.environ["RB200_WGRAD_TC"] = "1"
+print("wgrad (tcgen05) us", timeit(lambda i: wgrad(t.q_network.arena, ws["net"], batches[0].state.float_features, bench.B)))
+for dbg in (1, 2, 4, 8, 15, 7):
+    os.environ["RB200_WT_DBG"] = str(dbg)
+    print("  wgrad tcgen05 dbg=%d us" % dbg, timeit(lambda i: wgrad(t.q_network.arena, ws["net"], batches[0].state.float_features, bench.B)))
+os.environ["RB200_WT_DBG"] = "0"
+os.environ["RB200_WGRAD_TC"] = "0"
+print("wgrad (mma.sync) us", timeit(lambda i: wgrad(t.q_network.arena, ws["net"], batches[0].state.float_features, bench.B)))
+wgrad(t.q_network.arena, ws["net"], batches[0].state.float_features, bench.B)
 print("adam us", timeit(lambda i: (setattr(t.q_network.arena, "grad_ready", True), opt.fused_step(target=t.q_network_target.arena, tau=0.005))))
 print("full step us", timeit(lambda i: t.train_batch(rb.sample_discrete_dqn_batch(bench.B, bench.A))))

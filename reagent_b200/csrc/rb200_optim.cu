@@ -358,10 +358,14 @@ extern "C" int rb200_wgrad_splits(int batch) {
 int rb200_wgrad_tc_launch(const rb200_mlp_t* net, const float* net_input, int32_t batch,
                           const rb200_net_ws_t* ws, float* gpart, int32_t splits, void* stream);
 
+// The tcgen05 weight-gradient kernel (rb200_wgrad_tc.cu) is opt-in (RB200_WGRAD_TC=1): measured
+// inside the captured DQN update it ties with this file's mma.sync kernel (76.2 vs 75.5 us per
+// update at BASELINE config 2, round 2) -- both are bound by their prologue / epilogue at 128-row
+// slabs, not by the tensor pipe -- so the default stays the kernel with the longer track record.
 static bool wgrad_use_tc() {
   const char* d = getenv("RB200_DISABLE_TCGEN05");
   const char* w = getenv("RB200_WGRAD_TC");
-  return !(d && d[0] && d[0] != '0') && !(w && w[0] == '0');
+  return !(d && d[0] && d[0] != '0') && (w && w[0] == '1');
 }
 
 // Batch slabs for a network: enough (layer tile, slab) jobs to fill the 148 SMs about twice,

@@ -6,18 +6,22 @@
 // error compensation and the accumulator in Tensor Memory.
 //
 // The contraction runs over the BATCH, and both factors are stored batch-row-major in HBM
-// ([B, N] and [B, K]): read as UMMA operands they are "MN-major" -- 4 consecutive features are
-// the contiguous 16 bytes.  The kernel therefore stages a 32-row chunk of both matrices with
-// 16-byte cp.async pieces straight into the canonical MN-major no-swizzle layout
-//     [feature / 4][batch row][4 floats]      (feature-quad stride = SBO, 8-row group = LBO)
-// -- a pure address scatter, no transposition of values -- splits it in place into TF32 hi / lo
-// planes and issues, per 8-row k step,  D += A_hi.B_hi + A_lo.B_hi + A_hi.B_lo  with
-// M = 128 output features of dZ_l and N <= 256 input features of A_{l-1}.
+// ([B, N] and [B, K]), i.e. transposed with respect to the K-major operand layout the MMA
+// reads.  The kernel transposes while staging: a 32-row chunk of both matrices is loaded with
+// 16-byte loads (a lane = one row x 4 features; 16 rows x 32 B per instruction: whole sectors),
+// split into TF32 hi / lo in registers, and every scalar goes straight to its place in the
+// canonical K-major no-swizzle layout
+//     [batch row / 4][feature][4 batch rows]   (row-quad stride = LBO, 8 features = SBO = 128 B)
+// with bank-conflict-free 4-byte stores (the padded row-quad stride spreads a warp's 32 stores
+// over the 32 banks); every 8-row k step issues  D += A_hi.B_hi + A_lo.B_hi + A_hi.B_lo  with M = 128 output
+// features of dZ_l and N <= 256 input features of A_{l-1}.
 //
 // One CTA = (layer, 128-feature tile of dZ_l, 256-feature tile of A_{l-1}, batch slab); the
 // slabs are summed later by the Adam kernel in slab order (deterministic), exactly like the
 // mma.sync kernel this one replaces for shapes that fit (rb200_optim.cu keeps that kernel for
-// the rest).  Two smem stages: the copies + split of chunk c+1 overlap the MMAs of chunk c.
+// the rest).  Two smem stages; the loads of chunk c+1 are in flight while chunk c's MMAs run.
+#include <stdlib.h>
+
 #include "rb200_umma.cuh"
 
 namespace rb200 {
@@ -25,9 +29,10 @@ namespace rb200 {
 constexpr int kWtRows = 32;                       // batch rows per stage = 4 MMA k steps
 constexpr int kWtM = 128;                         // dZ features per tile (UMMA M)
 constexpr int kWtN = 256;                         // input features per tile (UMMA N, TMEM columns)
-constexpr int kWtQuad = kWtRows * 16 + 16;        // bytes per feature quad (+16: conflict-free scatter)
-constexpr int kWtPlaneA = (kWtM / 4) * kWtQuad;
-constexpr int kWtPlaneB = (kWtN / 4) * kWtQuad;
+constexpr int kWtQuadA = kWtM * 16 + 16;          // bytes per 4-row group of the dZ operand
+constexpr int kWtQuadB = kWtN * 16 + 16;          // ... of the activation operand
+constexpr int kWtPlaneA = (kWtRows / 4) * kWtQuadA;
+constexpr int kWtPlaneB = (kWtRows / 4) * kWtQuadB;
 constexpr int kWtStage = 2 * (kWtPlaneA + kWtPlaneB);  // A_hi, A_lo, B_hi, B_lo
 constexpr int kWtThreads = 256;
 constexpr int kWtSmem = 2 * kWtStage + 64;
@@ -40,21 +45,13 @@ struct WtLayer {
   int tiles_m, tiles_k, job_start;
 };
 struct WtParams {
+  int dbg;  // profiling only: 1 skip the loads, 2 skip the split, 4 skip the MMAs, 8 skip the epilogue stores
   int n_layers;
   WtLayer L[kMaxLayers];
   int B, rows_per_split;
   float* gpart;
   long long P;
 };
-
-// K-major/MN-major agnostic descriptor: (start, "leading" and "stride" byte offsets), version 1
-__device__ __forceinline__ uint64_t wt_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return umma_desc(saddr, lbo, sbo);
-}
-// kind::tf32, fp32 accumulate, A and B MN-major (bits 15 / 16), M x N
-__device__ __forceinline__ uint32_t wt_idesc(int M, int N) {
-  return umma_idesc_tf32(M, N) | (1u << 15) | (1u << 16);
-}
 
 __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const WtParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -68,7 +65,6 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const WtParams 
   const int N = Ly.N, K = Ly.K;
   const int nrows_m = min(kWtM, N - n0);             // valid dZ features of this tile
   const int ncols = min(kWtN, K - k0);               // valid input features of this tile
-  const int nq_a = ceil_div(nrows_m, 4), nq_b = ceil_div(ncols, 4);
   const int n_mma = (ncols + 15) & ~15;              // UMMA N (multiple of 16 for M = 128)
   const int split = blockIdx.y;
   const int b_begin = split * p.rows_per_split;
@@ -79,9 +75,9 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const WtParams 
   uint64_t* acc_done = mma_done + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
-  // operand padding (features past the matrix, rows past the slab) must be finite zeros
-  for (int i = tid * 16; i < 2 * kWtStage; i += kWtThreads * 16)
-    *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  // No zero-fill of the stages: every staged feature row is rewritten per chunk (zeros past the
+  // slab end); features past the matrix are never written, and whatever they hold only reaches
+  // accumulator rows / columns that are not stored (D[m][n] depends on A row m and B row n only).
   if (tid == 0) {
     mbar_init(mma_done, 1);
     mbar_init(mma_done + 1, 1);
@@ -99,83 +95,102 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const WtParams 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const bool vz = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(Ly.dZ) & 15) == 0);
-  const bool va = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(Ly.A) & 15) == 0);
-  // raw fp32 chunk -> hi planes of stage `st` (16-byte pieces, MN-major scatter)
-  auto stage_load = [&](int c, int st) {
-    unsigned char* base = smem + st * kWtStage;
+  // A chunk (32 batch rows) is moved in "units" of 16 rows x 8 features: lane = (row, 4-feature
+  // piece) loads one float4 (16 rows x 32 B: whole sectors), splits it into TF32 hi / lo and
+  // stores the 2 x 4 scalars transposed into the K-major planes -- element (row r, feature f)
+  // at [r / 4][f][r % 4].  With the 16-byte padded row-quad stride the 32 stores of a warp hit
+  // 32 different banks.  Units of a chunk: 2 halves x (feature pairs of A + of B), dealt to the
+  // 8 warps round-robin; the loads of chunk c+1 are in flight while chunk c's MMAs run.
+  const int fa = (nrows_m + 7) & ~7, fb = (ncols + 7) & ~7;  // staged features (multiples of 8)
+  const int ua = 2 * (fa / 8), utotal = ua + 2 * (fb / 8);
+  constexpr int kMaxUnits = (2 * (kWtM / 8) + 2 * (kWtN / 8)) / (kWtThreads / 32);  // 12
+  const int r_l = lane & 15, qsel = lane >> 4;
+  float4 regs[kMaxUnits];
+  auto chunk_fetch = [&](int c) {
     const int r0 = b_begin + c * kWtRows;
-    for (int idx = tid; idx < kWtRows * (nq_a + nq_b); idx += kWtThreads) {
-      const bool isb = idx >= kWtRows * nq_a;
-      const int j = isb ? idx - kWtRows * nq_a : idx;
-      const int nq = isb ? nq_b : nq_a;
-      const int r = j / nq, q = j - r * nq;
-      const int row = r0 + r;
-      const int f = (isb ? k0 : n0) + 4 * q;          // first feature of the piece
-      const int F = isb ? K : N;
-      const float* src = (isb ? Ly.A : Ly.dZ) + (size_t)row * F + f;
-      float* dst = reinterpret_cast<float*>(base + (isb ? 2 * kWtPlaneA : 0) + q * kWtQuad + r * 16);
-      if (row < b_end && (isb ? va : vz) && f + 3 < F) {
-        cp_async16(dst, src);
-      } else {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < b_end) {
-          if (f < F) v.x = src[0];
-          if (f + 1 < F) v.y = src[1];
-          if (f + 2 < F) v.z = src[2];
-          if (f + 3 < F) v.w = src[3];
+#pragma unroll
+    for (int u = 0; u < kMaxUnits; ++u) {
+      const int unit = warp + u * (kWtThreads / 32);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (unit < utotal && !(p.dbg & 1)) {
+        const bool isb = unit >= ua;
+        const int j = isb ? unit - ua : unit;
+        const int h = j & 1, fp = j >> 1;
+        const int row = r0 + 16 * h + r_l;
+        const int f = (isb ? k0 : n0) + 8 * fp + 4 * qsel;
+        const int F = isb ? K : N;
+        if (row < b_end && f < F) {
+          const float* src = (isb ? Ly.A : Ly.dZ) + (size_t)row * F + f;
+          if (f + 3 < F && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+            v = __ldg(reinterpret_cast<const float4*>(src));
+          } else {
+            v.x = src[0];
+            if (f + 1 < F) v.y = src[1];
+            if (f + 2 < F) v.z = src[2];
+            if (f + 3 < F) v.w = src[3];
+          }
         }
-        *reinterpret_cast<float4*>(dst) = v;
       }
+      regs[u] = v;
     }
   };
-  // hi planes -> (hi, lo) in place; also the bias-gradient partial of this thread's feature
-  float bsum = 0.f;
-  auto stage_split = [&](int st) {
+  auto chunk_store = [&](int st) {
     unsigned char* base = smem + st * kWtStage;
-    if (tk == 0 && tid < kWtM) {  // raw values are still intact here
-      const float* col = reinterpret_cast<const float*>(base + (tid >> 2) * kWtQuad) + (tid & 3);
-#pragma unroll 8
-      for (int r = 0; r < kWtRows; ++r) bsum += col[r * 4];
-    }
-    __syncthreads();
-    for (int idx = tid; idx < kWtRows * (nq_a + nq_b); idx += kWtThreads) {
-      const bool isb = idx >= kWtRows * nq_a;
-      const int j = isb ? idx - kWtRows * nq_a : idx;
-      const int q = j / kWtRows, r = j - q * kWtRows;
-      float* hi = reinterpret_cast<float*>(base + (isb ? 2 * kWtPlaneA : 0) + q * kWtQuad + r * 16);
+#pragma unroll
+    for (int u = 0; u < kMaxUnits; ++u) {
+      const int unit = warp + u * (kWtThreads / 32);
+      if (unit >= utotal) continue;
+      const bool isb = unit >= ua;
+      const int j = isb ? unit - ua : unit;
+      const int h = j & 1, fp = j >> 1;
+      const int r = 16 * h + r_l;
+      const int fl = 8 * fp + 4 * qsel;
+      float* hi = reinterpret_cast<float*>(base + (isb ? 2 * kWtPlaneA + (r >> 2) * kWtQuadB
+                                                       : (r >> 2) * kWtQuadA) + fl * 16) + (r & 3);
       float* lo = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(hi) + (isb ? kWtPlaneB : kWtPlaneA));
-      float4 h, l;
-      split4(*reinterpret_cast<const float4*>(hi), h, l);
-      *reinterpret_cast<float4*>(hi) = h;
-      *reinterpret_cast<float4*>(lo) = l;
+      float4 hh, ll;
+      split4(regs[u], hh, ll);
+      hi[0] = hh.x; hi[4] = hh.y; hi[8] = hh.z; hi[12] = hh.w;
+      lo[0] = ll.x; lo[4] = ll.y; lo[8] = ll.z; lo[12] = ll.w;
+    }
+  };
+  // bias gradient: column sums of dZ over the chunk (hi + lo is the exact value)
+  float bsum = 0.f;
+  auto chunk_bias = [&](int st) {
+    if (tk != 0 || tid >= kWtM) return;
+    const unsigned char* base = smem + st * kWtStage;
+#pragma unroll
+    for (int rq = 0; rq < kWtRows / 4; ++rq) {
+      const float4 a = *reinterpret_cast<const float4*>(base + rq * kWtQuadA + tid * 16);
+      const float4 b = *reinterpret_cast<const float4*>(base + kWtPlaneA + rq * kWtQuadA + tid * 16);
+      bsum += ((a.x + b.x) + (a.y + b.y)) + ((a.z + b.z) + (a.w + b.w));
     }
   };
 
-  const uint32_t idesc = wt_idesc(kWtM, n_mma);
+  const uint32_t idesc = umma_idesc_tf32(kWtM, n_mma);
   uint32_t done_par[2] = {0u, 0u};
-  if (nchunks > 0) {
-    stage_load(0, 0);
-    cp_async_commit();
-  }
+  if (nchunks > 0) chunk_fetch(0);
   for (int c = 0; c < nchunks; ++c) {
     const int st = c & 1;
-    cp_async_wait<0>();
-    __syncthreads();
-    stage_split(st);
+    if (c >= 2) {  // the MMAs of chunk c-2 read this stage
+      mbar_wait(mma_done + st, done_par[st]);
+      done_par[st] ^= 1u;
+    }
+    if (!(p.dbg & 2)) chunk_store(st);
+    if (c + 1 < nchunks) chunk_fetch(c + 1);  // in flight during the barrier and the MMAs
     fence_proxy_async_smem();
     __syncthreads();
+    chunk_bias(st);
     if (tid == 0) {
       tc_fence_after();
       const uint32_t sb = smem_u32(smem + st * kWtStage);
       const uint32_t a_hi = sb, a_lo = sb + kWtPlaneA, b_hi = sb + 2 * kWtPlaneA, b_lo = b_hi + kWtPlaneB;
 #pragma unroll
-      for (int ks = 0; ks < kWtRows / 8; ++ks) {
-        const uint32_t o = ks * 128;  // 8 batch rows x 16 B inside every feature quad
-        // MN-major no-swizzle: "leading" offset = next group of 8 k (128 B), "stride" offset =
-        // next group of 4 features (the quad stride)
-        const uint64_t dah = wt_desc(a_hi + o, 128, kWtQuad), dal = wt_desc(a_lo + o, 128, kWtQuad);
-        const uint64_t dbh = wt_desc(b_hi + o, 128, kWtQuad), dbl = wt_desc(b_lo + o, 128, kWtQuad);
+      for (int ks = 0; ks < ((p.dbg & 4) ? 0 : kWtRows / 8); ++ks) {
+        // K-major no-swizzle: leading offset = next 4-row group, stride offset = 8 features
+        const uint32_t oa = ks * 2 * kWtQuadA, ob = ks * 2 * kWtQuadB;
+        const uint64_t dah = umma_desc(a_hi + oa, kWtQuadA, 128), dal = umma_desc(a_lo + oa, kWtQuadA, 128);
+        const uint64_t dbh = umma_desc(b_hi + ob, kWtQuadB, 128), dbl = umma_desc(b_lo + ob, kWtQuadB, 128);
         umma_tf32(tmem, dah, dbh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
         umma_tf32(tmem, dal, dbh, idesc, 1u);
         umma_tf32(tmem, dah, dbl, idesc, 1u);
@@ -183,26 +198,21 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const WtParams 
       umma_commit(mma_done + st);
       if (c == nchunks - 1) umma_commit(acc_done);
     }
-    // the next chunk goes into the other stage once ITS previous MMAs (chunk c-1) retired
-    if (c + 1 < nchunks) {
-      if (c >= 1) {
-        mbar_wait(mma_done + (st ^ 1), done_par[st ^ 1]);
-        done_par[st ^ 1] ^= 1u;
-      }
-      stage_load(c + 1, st ^ 1);
-      cp_async_commit();
-    }
   }
 
-  // ---- epilogue: accumulator -> this slab's gradient partial ----
+  // ---- epilogue: accumulator -> shared memory (the operand stages are dead) -> this slab's
+  // gradient partial with coalesced 16-byte stores (a thread owns a TMEM lane = a row of dW;
+  // writing it straight out would be 4-byte pieces 1 KB apart) ----
   float* gp = p.gpart + (size_t)split * p.P;
+  constexpr int kLdT = kWtN + 4;  // floats per staged row: 16-byte aligned, conflict-free
+  float* tile = reinterpret_cast<float*>(smem);
   if (nchunks > 0) {
     mbar_wait(acc_done, 0);
     tc_fence_after();
   }
   if (warp < 4) {
-    const int n = n0 + warp * 32 + lane;
-    for (int c0 = 0; c0 < ncols; c0 += 16) {
+    const int nl = warp * 32 + lane;
+    for (int c0 = 0; c0 < n_mma; c0 += 16) {
       uint32_t v[16];
       if (nchunks > 0) {
         asm volatile(
@@ -217,14 +227,28 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const WtParams 
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0u;
       }
-      if (n < N) {
-        float* dst = gp + Ly.w_off + (size_t)n * K + k0 + c0;
+      float4* d = reinterpret_cast<float4*>(tile + (size_t)nl * kLdT + c0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c0 + j < ncols) dst[j] = __uint_as_float(v[j]);
+      for (int j = 0; j < 4; ++j)
+        d[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+    }
+    if (tk == 0 && n0 + nl < N) gp[Ly.b_off + n0 + nl] = bsum;
+  }
+  __syncthreads();
+  {
+    const bool v4 = ((K & 3) == 0) && ((k0 & 3) == 0) && ((Ly.w_off & 3) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(gp) & 15) == 0);
+    for (int r = warp; r < ((p.dbg & 8) ? 0 : nrows_m); r += kWtThreads / 32) {
+      float* dst = gp + Ly.w_off + (size_t)(n0 + r) * K + k0;
+      const float* src = tile + (size_t)r * kLdT;
+      if (v4) {
+        for (int c = lane * 4; c < ncols; c += 128)
+          *reinterpret_cast<float4*>(dst + c) = *reinterpret_cast<const float4*>(src + c);
+      } else {
+        for (int c = lane; c < ncols; c += 32) dst[c] = src[c];
       }
     }
-    if (tk == 0 && n < N) gp[Ly.b_off + n] = bsum;
   }
   tc_fence_before();
   __syncthreads();
@@ -242,6 +266,7 @@ using namespace rb200;
 int rb200_wgrad_tc_launch(const rb200_mlp_t* net, const float* net_input, int32_t batch,
                           const rb200_net_ws_t* ws, float* gpart, int32_t splits, void* stream) {
   WtParams p = {};
+  { const char* e = getenv("RB200_WT_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.n_layers = net->n_layers;
   p.B = batch;
   p.rows_per_split = ceil_div(ceil_div(batch, splits), kWtRows) * kWtRows;

@@ -541,3 +541,16 @@ def test_dqn_cpe_gradients_match_reference():
     for i, g in enumerate(param_grads(t.q_network_cpe.arena, list(t.q_network_cpe.parameters()))):
         assert G.rel_err(g, arrays[f"grad0c.{i}"]) < TOL, f"cpe grad {i}"
     assert abs(float(l1) - arrays["cpe_losses"][0][0]) <= TOL * max(1.0, abs(arrays["cpe_losses"][0][0]))
+
+
+@pytest.mark.parametrize("name", ["dqn_huber_double", "dqn_timediff_odd_dims", "dqn_cartpole_config0"])
+def test_tcgen05_weight_gradient_kernel_matches_reference(name, monkeypatch):
+    """The opt-in tcgen05 weight-gradient kernel (RB200_WGRAD_TC=1, csrc/rb200_wgrad_tc.cu)
+    against the reference's gradients: 1e-5, like the default mma.sync kernel."""
+    monkeypatch.setenv("RB200_WGRAD_TC", "1")
+    arrays, meta = G.load(name)
+    t = _build_trainer(meta, arrays)
+    batch = _rlt_batch(G.batch_tensors(arrays, "cuda"), meta)
+    t._td_step(batch)
+    for i, g in enumerate(t.q_network_grads()):
+        assert G.rel_err(g, arrays[f"grad0.{i}"]) < TOL, f"grad {i}"
