@@ -226,6 +226,58 @@ typedef struct rb200_cpe_args {
 int rb200_cpe_heads(const rb200_cpe_args_t* args, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* Loss heads of ParametricDQNTrainer and C51Trainer (rb200_heads.cu); the networks */
+/* around them run on rb200_mlp_forward / rb200_linear_forward / *_backward / wgrad. */
+/*   rb200_pdqn_head: reagent/training/parametric_dqn_trainer.py:109-173 (TD target    */
+/*     from the tiled possible next actions or the SARSA value, mse | huber, dL/dq)     */
+/*   rb200_c51_head:  reagent/training/c51_trainer.py:98-173 (log-softmax over atoms,  */
+/*     masked arg max of expected values, categorical projection, cross entropy,       */
+/*     dL/dlogits); reagent/models/categorical_dqn.py:28-35                             */
+/* ------------------------------------------------------------------------- */
+typedef struct rb200_pdqn_args {
+  int32_t batch, max_num_action;   /* M tiled next actions per row; 0 = SARSA */
+  const float* next_q;             /* [B*M] q_network(tiled s', a') (double-Q) or NULL */
+  const float* next_q_target;      /* [B*M] (maxq) or [B] (SARSA: q_target(s', next_action)) */
+  const float* mask;               /* [B,M] possible_next_actions_mask or NULL */
+  const float* reward;             /* [B] */
+  const float* not_terminal;       /* [B] */
+  const float* discount_src;       /* [B] or NULL */
+  float gamma;
+  int32_t discount_mode, double_q, loss_kind;
+  const float* q_values;           /* [B] q_network(state, action) */
+  float* dz;                       /* [B] d loss / d q */
+  float* td_target;                /* [B] or NULL */
+  float* loss_partials;            /* [ceil(B/256)] */
+  float* loss;                     /* [1] */
+  uint32_t* tile_counter;
+} rb200_pdqn_args_t;
+int rb200_pdqn_head(const rb200_pdqn_args_t* args, void* stream);
+
+typedef struct rb200_c51_args {
+  int32_t batch, num_actions, num_atoms;
+  const float* logits_next_online; /* [B, A*N] distributional_network(next_state), online (double-Q) or NULL */
+  const float* logits_next_target; /* [B, A*N] target network */
+  const float* logits_cur;         /* [B, A*N] online network on state */
+  const float* action;             /* [B,A] */
+  const float* next_action;        /* [B,A] (SARSA) or NULL */
+  const float* possible_next_actions_mask; /* [B,A] or NULL */
+  const float* reward;             /* [B] */
+  const float* not_terminal;       /* [B] */
+  const float* discount_src;       /* [B] or NULL: gamma ** discount_src */
+  const float* reward_boost;       /* [A] or NULL */
+  const float* support;            /* [N] torch.linspace(qmin, qmax, N) */
+  float gamma, qmin, qmax, scale_support;
+  int32_t double_q, maxq;
+  float* dz_logits;                /* [B, A*N] */
+  float* all_q_values;             /* [B,A] or NULL */
+  int32_t* next_action_idx;        /* [B] or NULL */
+  float* loss_partials;            /* [B] */
+  float* loss;                     /* [1] */
+  uint32_t* tile_counter;
+} rb200_c51_args_t;
+int rb200_c51_head(const rb200_c51_args_t* args, void* stream);
+
+/* ------------------------------------------------------------------------- */
 /* QR-DQN (reagent/training/qrdqn_trainer.py:108-194).  The [hidden -> A*N] head  */
 /* is too wide for a row tile, so it runs as 2-D tiled launches:                   */
 /*   rb200_linear_forward      out = act(in . W^T + b), any N     (nn.Linear fwd) */

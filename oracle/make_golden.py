@@ -465,6 +465,140 @@ def normalization_case(name, seed=0, n=2000):
 
 
 # ---------------------------------------------------------------------------
+# ParametricDQNTrainer / C51Trainer
+# ---------------------------------------------------------------------------
+def pdqn_case(name, *, B=24, S=6, AD=3, M=4, sizes=(16, 10), acts=("relu", "tanh"), loss="mse",
+              double_q=True, maxq=True, multi_steps=None, with_reward_net=False, gamma=0.95,
+              tau=0.05, lr=1e-2, seed=0):
+    rlt = ref("reagent.core.types")
+    params = ref("reagent.core.parameters")
+    critic = ref("reagent.models.critic")
+    tr = ref("reagent.training.parametric_dqn_trainer")
+    union = ref("reagent.optimizer.union")
+    torch.manual_seed(seed)
+    q = critic.FullyConnectedCritic(S, AD, list(sizes), list(acts))
+    _perturb(q)
+    qt = q.get_target_network()
+    _perturb(qt, 0.05)
+    rn = None
+    if with_reward_net:
+        rn = critic.FullyConnectedCritic(S, AD, list(sizes), list(acts))
+        _perturb(rn)
+    rl = params.RLParameters(gamma=gamma, target_update_rate=tau, q_network_loss=loss,
+                             maxq_learning=maxq, multi_steps=multi_steps)
+    trainer = tr.ParametricDQNTrainer(
+        q, qt, rn, rl=rl, double_q_learning=double_q,
+        optimizer=union.Optimizer__Union(Adam=union.classes["Adam"](lr=lr)))
+    nt = (torch.rand(B, 1) > 0.2).float()
+    pnam = (torch.rand(B, M) > 0.3).float()
+    pnam[torch.arange(B), torch.randint(M, (B,))] = 1.0
+    batch = dict(state=torch.randn(B, S), next_state=torch.randn(B, S), reward=torch.randn(B, 1),
+                 not_terminal=nt, action=torch.randn(B, AD), next_action=torch.randn(B, AD),
+                 possible_actions=torch.randn(B * M, AD), possible_actions_mask=torch.ones(B, M),
+                 possible_next_actions=torch.randn(B * M, AD), possible_next_actions_mask=pnam,
+                 time_diff=torch.ones(B, 1), step=torch.randint(1, 4, (B, 1)))
+    rbatch = rlt.ParametricDqnInput(
+        state=rlt.FeatureData(batch["state"]), next_state=rlt.FeatureData(batch["next_state"]),
+        reward=batch["reward"], time_diff=batch["time_diff"],
+        step=batch["step"] if multi_steps is not None else None, not_terminal=nt,
+        action=rlt.FeatureData(batch["action"]), next_action=rlt.FeatureData(batch["next_action"]),
+        possible_actions=rlt.FeatureData(batch["possible_actions"]),
+        possible_actions_mask=batch["possible_actions_mask"],
+        possible_next_actions=rlt.FeatureData(batch["possible_next_actions"]),
+        possible_next_actions_mask=pnam, extras=rlt.ExtraData())
+    arrays = {f"batch.{k}": _np(v) for k, v in batch.items()}
+    _dump_net(arrays, "q0", q)
+    _dump_net(arrays, "qt0", qt)
+    if rn is not None:
+        _dump_net(arrays, "r0", rn)
+    opts = [o["optimizer"] for o in trainer.configure_optimizers()]
+    losses = []
+    for it in range(N_UPDATES):
+        cap = {}
+        out = run_update(trainer, rbatch, it, opts, capture=cap)
+        losses.append([x for x in out[:-1]])
+        if it == 0:
+            for i, g in enumerate(cap[0]):
+                arrays[f"grad0.{i}"] = _np(g)
+    arrays["losses"] = np.array(losses, dtype=np.float64)
+    _dump_net(arrays, "qN", q)
+    _dump_net(arrays, "qtN", qt)
+    if rn is not None:
+        _dump_net(arrays, "rN", rn)
+    _save(name, arrays, dict(kind="pdqn", B=B, S=S, AD=AD, M=M, sizes=list(sizes), acts=list(acts),
+                             loss=loss, double_q=double_q, maxq=maxq, multi_steps=multi_steps,
+                             with_reward_net=with_reward_net, gamma=gamma, tau=tau, lr=lr,
+                             n_updates=N_UPDATES))
+
+
+def c51_case(name, *, B=24, S=8, A=4, N=11, sizes=(16, 12), acts=("relu", "relu"), double_q=True,
+             maxq=True, multi_steps=None, random_masks=False, qmin=-3.0, qmax=5.0, boost=None,
+             gamma=0.9, tau=0.05, lr=1e-2, seed=0):
+    rlt = ref("reagent.core.types")
+    params = ref("reagent.core.parameters")
+    dqn_mod = ref("reagent.models.dqn")
+    cat = ref("reagent.models.categorical_dqn")
+    tr = ref("reagent.training.c51_trainer")
+    union = ref("reagent.optimizer.union")
+    torch.manual_seed(seed)
+    dist = dqn_mod.FullyConnectedDQN(S, A, list(sizes), list(acts), num_atoms=N)
+    with torch.no_grad():
+        for _, b in _fc_params(dist):
+            b.normal_(0, 0.1)
+    q = cat.CategoricalDQN(dist, qmin=qmin, qmax=qmax, num_atoms=N)
+    qt = q.get_target_network()
+    with torch.no_grad():
+        for w, b in _fc_params(qt.distributional_network):
+            w.add_(torch.randn_like(w) * 0.05)
+            b.add_(torch.randn_like(b) * 0.05)
+    rl = params.RLParameters(gamma=gamma, target_update_rate=tau, maxq_learning=maxq,
+                             multi_steps=multi_steps, reward_boost=boost)
+    trainer = tr.C51Trainer(q, qt, actions=[str(i) for i in range(A)], rl=rl,
+                            double_q_learning=double_q, minibatch_size=B, num_atoms=N, qmin=qmin,
+                            qmax=qmax, optimizer=union.Optimizer__Union(Adam=union.classes["Adam"](lr=lr)))
+    act_idx, nact_idx = torch.randint(A, (B,)), torch.randint(A, (B,))
+    nt = (torch.rand(B, 1) > 0.2).float()
+    pnam = torch.ones(B, A)
+    if random_masks:
+        pnam = (torch.rand(B, A) > 0.3).float()
+        pnam[torch.arange(B), torch.randint(A, (B,))] = 1.0
+    # rewards on and between support points: exercises the l == b == u corner cases
+    reward = torch.randn(B, 1)
+    reward[: B // 4] = torch.round(reward[: B // 4])
+    batch = dict(state=torch.randn(B, S), next_state=torch.randn(B, S), reward=reward,
+                 time_diff=torch.ones(B, 1), step=torch.randint(1, 4, (B, 1)), not_terminal=nt,
+                 action=torch.nn.functional.one_hot(act_idx, A).float(),
+                 next_action=torch.nn.functional.one_hot(nact_idx, A).float() * nt,
+                 possible_actions_mask=torch.ones(B, A), possible_next_actions_mask=pnam)
+    rbatch = rlt.DiscreteDqnInput(
+        state=rlt.FeatureData(batch["state"]), next_state=rlt.FeatureData(batch["next_state"]),
+        reward=batch["reward"], time_diff=batch["time_diff"],
+        step=batch["step"] if multi_steps is not None else None, not_terminal=nt,
+        action=batch["action"], next_action=batch["next_action"],
+        possible_actions_mask=batch["possible_actions_mask"], possible_next_actions_mask=pnam,
+        extras=rlt.ExtraData(action_probability=torch.ones(B, 1)))
+    arrays = {f"batch.{k}": _np(v) for k, v in batch.items()}
+    _dump_net(arrays, "q0", q.distributional_network)
+    _dump_net(arrays, "qt0", qt.distributional_network)
+    opts = [o["optimizer"] for o in trainer.configure_optimizers()]
+    losses = []
+    for it in range(N_UPDATES):
+        cap = {}
+        out = run_update(trainer, rbatch, it, opts, capture=cap)
+        losses.append(out[0])
+        if it == 0:
+            for i, g in enumerate(cap[0]):
+                arrays[f"grad0.{i}"] = _np(g)
+    arrays["losses"] = np.array(losses, dtype=np.float64)
+    _dump_net(arrays, "qN", q.distributional_network)
+    _dump_net(arrays, "qtN", qt.distributional_network)
+    _save(name, arrays, dict(kind="c51", B=B, S=S, A=A, N=N, sizes=list(sizes), acts=list(acts),
+                             double_q=double_q, maxq=maxq, multi_steps=multi_steps, qmin=qmin,
+                             qmax=qmax, boost=boost, gamma=gamma, tau=tau, lr=lr,
+                             n_updates=N_UPDATES))
+
+
+# ---------------------------------------------------------------------------
 # dense preprocessor
 # ---------------------------------------------------------------------------
 def preprocessor_case(name, seed=0, B=64):
@@ -794,6 +928,12 @@ def main(only=None):
     add(dqn_case, "dqn_cpe_huber", cpe_metrics=["m1"], seed=8, random_masks=True, temperature=0.5)
     add(dqn_case, "dqn_cpe_mse_sarsa_multistep", cpe_metrics=[], loss="mse", maxq=False,
         multi_steps=3, seed=9, B=37, S=7, A=3, sizes=(10, 6), temperature=1.0)
+    add(pdqn_case, "pdqn_double_mse")
+    add(pdqn_case, "pdqn_sarsa_huber_reward", maxq=False, loss="huber", with_reward_net=True, seed=1)
+    add(pdqn_case, "pdqn_single_multistep", double_q=False, multi_steps=3, seed=2, B=19, S=5, AD=2, M=3)
+    add(c51_case, "c51_double")
+    add(c51_case, "c51_single_masked_boost", double_q=False, random_masks=True, boost={"1": 0.5}, seed=1)
+    add(c51_case, "c51_sarsa_multistep", maxq=False, multi_steps=3, seed=2, N=7, acts=("tanh", "relu"))
     add(replay_case, "replay_uniform_h1", prioritized=False, cap=100, n_add=73, B=16)
     add(replay_case, "replay_uniform_h3_wrap", prioritized=False, cap=64, n_add=150, B=32, horizon=3, seed=1, with_extra=True)
     add(replay_case, "replay_uniform_h5_cont", prioritized=False, cap=128, n_add=300, B=24, horizon=5, seed=2, continuous=True, gamma=0.97)

@@ -435,3 +435,100 @@ def qrdqn_update(q: Net, qt: Net, adam: AdamState, batch, *, gamma, tau, num_ato
     adam.step(params, grads)
     soft_update(qt, q, tau)
     return float(loss.detach()), grads, aux
+
+
+# ---------------------------------------------------------------------------
+# ParametricDQN (reagent/training/parametric_dqn_trainer.py:109-214)
+# ---------------------------------------------------------------------------
+def pdqn_update(q: Net, qt: Net, adam: AdamState, batch, *, gamma, tau, double_q=True, maxq=True,
+                loss="mse", discount_src=None, reward_net: Optional[Net] = None,
+                adam_r: Optional[AdamState] = None):
+    """One ParametricDQNTrainer update.  batch: state/next_state (B,S), action/next_action (B,Ad),
+    possible_next_actions (B*M,Ad), possible_next_actions_mask (B,M), reward/not_terminal (B,1).
+    Returns (td_loss, reward_loss | None, grads of q)."""
+    reward, not_terminal = batch["reward"], batch["not_terminal"].float()
+    B = reward.shape[0]
+    discount = torch.full_like(reward, gamma)
+    if discount_src is not None:
+        discount = torch.pow(gamma, discount_src.float())
+    with torch.no_grad():
+        if maxq:
+            pna = batch["possible_next_actions"]
+            M = pna.shape[0] // B
+            tiled = batch["next_state"].repeat_interleave(M, dim=0)  # get_tiled_batch
+            all_q, all_qt = critic(q, tiled, pna), critic(qt, tiled, pna)
+            mask = batch["possible_next_actions_mask"].float()
+            qv = all_q.reshape(mask.shape) + ACTION_NOT_POSSIBLE_VAL * (1 - mask)
+            qtv = all_qt.reshape(mask.shape) + ACTION_NOT_POSSIBLE_VAL * (1 - mask)
+            if double_q:
+                _, idx = torch.max(qv, dim=1, keepdim=True)
+                next_q = torch.gather(qtv, 1, idx)
+            else:
+                next_q, _ = torch.max(qtv, dim=1, keepdim=True)
+        else:
+            next_q = critic(qt, batch["next_state"], batch["next_action"])
+    target = reward + not_terminal * discount * next_q
+    fn = F.mse_loss if loss == "mse" else F.smooth_l1_loss
+    params = net_params(q)
+    td = fn(critic(q, batch["state"], batch["action"]), target)
+    grads = [g.detach().clone() for g in torch.autograd.grad(td, params)]
+    adam.step(params, grads)
+    rl = None
+    if reward_net is not None:
+        mrc = reward if batch.get("metrics") is None else torch.cat((reward, batch["metrics"]), dim=1)
+        est = critic(reward_net, batch["state"], batch["action"])
+        rloss = F.mse_loss(est.squeeze(-1), mrc.squeeze(-1))
+        pr = net_params(reward_net)
+        adam_r.step(pr, [g.detach().clone() for g in torch.autograd.grad(rloss, pr)])
+        rl = float(rloss.detach())
+    soft_update(qt, q, tau)
+    return float(td.detach()), rl, grads
+
+
+# ---------------------------------------------------------------------------
+# C51 (reagent/training/c51_trainer.py:98-173, reagent/models/categorical_dqn.py:28-35)
+# ---------------------------------------------------------------------------
+def c51_loss(q: Net, qt: Net, batch, *, gamma, num_atoms, qmin, qmax, double_q=True, maxq=True,
+             discount_src=None, reward_boost=None):
+    reward, action = batch["reward"], batch["action"]
+    B, A, N = reward.shape[0], action.shape[1], num_atoms
+    support = torch.linspace(qmin, qmax, N)
+    scale_support = (qmax - qmin) / (N - 1.0)
+    if reward_boost is not None:
+        reward = reward + torch.sum(action.float() * reward_boost, dim=1, keepdim=True)
+    discount = torch.full_like(reward, gamma)
+    if discount_src is not None:
+        discount = torch.pow(gamma, discount_src.float())
+    not_terminal = batch["not_terminal"].float()
+    log_dist = lambda net, x: F.log_softmax(mlp(net, x).view(B, A, N), -1)  # noqa: E731
+    with torch.no_grad():
+        next_dist = log_dist(qt, batch["next_state"]).exp()
+        if maxq:
+            if double_q:
+                next_q = (log_dist(q, batch["next_state"]).exp() * support).sum(2)
+            else:
+                next_q = (next_dist * support).sum(2)
+            mask = batch["possible_next_actions_mask"].float()
+            next_action = (next_q + ACTION_NOT_POSSIBLE_VAL * (1 - mask)).argmax(1)
+            next_dist = next_dist[range(B), next_action.reshape(-1)]
+        else:
+            next_dist = (next_dist * batch["next_action"].unsqueeze(-1)).sum(1)
+        target_Q = (reward + discount * not_terminal * support).clamp(qmin, qmax)
+        b = (target_Q - qmin) / scale_support
+        lo, up = b.floor().to(torch.int64), b.ceil().to(torch.int64)
+        lo[(up > 0) * (lo == up)] -= 1
+        up[(lo < (N - 1)) * (lo == up)] += 1
+        m = torch.zeros_like(next_dist)
+        m.scatter_add_(dim=1, index=lo, src=next_dist * (up.float() - b))
+        m.scatter_add_(dim=1, index=up, src=next_dist * (b - lo.float()))
+    ld = (log_dist(q, batch["state"]) * action.unsqueeze(-1)).sum(1)
+    return -(m * ld).sum(1).mean()
+
+
+def c51_update(q: Net, qt: Net, adam: AdamState, batch, *, gamma, tau, **kw):
+    params = net_params(q)
+    loss = c51_loss(q, qt, batch, gamma=gamma, **kw)
+    grads = [g.detach().clone() for g in torch.autograd.grad(loss, params)]
+    adam.step(params, grads)
+    soft_update(qt, q, tau)
+    return float(loss.detach()), grads

@@ -155,6 +155,26 @@ class SampleArgsT(C.Structure):
     ]
 
 
+class PdqnArgsT(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("max_num_action", C.c_int32), ("next_q", _vp),
+                ("next_q_target", _vp), ("mask", _vp), ("reward", _vp), ("not_terminal", _vp),
+                ("discount_src", _vp), ("gamma", C.c_float), ("discount_mode", C.c_int32),
+                ("double_q", C.c_int32), ("loss_kind", C.c_int32), ("q_values", _vp), ("dz", _vp),
+                ("td_target", _vp), ("loss_partials", _vp), ("loss", _vp), ("tile_counter", _vp)]
+
+
+class C51ArgsT(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("num_actions", C.c_int32), ("num_atoms", C.c_int32),
+                ("logits_next_online", _vp), ("logits_next_target", _vp), ("logits_cur", _vp),
+                ("action", _vp), ("next_action", _vp), ("possible_next_actions_mask", _vp),
+                ("reward", _vp), ("not_terminal", _vp), ("discount_src", _vp),
+                ("reward_boost", _vp), ("support", _vp), ("gamma", C.c_float), ("qmin", C.c_float),
+                ("qmax", C.c_float), ("scale_support", C.c_float), ("double_q", C.c_int32),
+                ("maxq", C.c_int32), ("dz_logits", _vp), ("all_q_values", _vp),
+                ("next_action_idx", _vp), ("loss_partials", _vp), ("loss", _vp),
+                ("tile_counter", _vp)]
+
+
 class CpeArgsT(C.Structure):
     _fields_ = [("batch", C.c_int32), ("num_actions", C.c_int32), ("num_metrics", C.c_int32),
                 ("next_scores", _vp), ("mask", _vp), ("temperature", C.c_float), ("action", _vp),
@@ -263,6 +283,8 @@ def _declare(lib):
     lib.rb200_adam_soft_update.argtypes = [C.POINTER(AdamArgsT), _vp]
     lib.rb200_soft_update.argtypes = [_vp, _vp, C.c_int64, C.c_float, C.c_float, _vp]
     lib.rb200_cpe_heads.argtypes = [C.POINTER(CpeArgsT), _vp]
+    lib.rb200_pdqn_head.argtypes = [C.POINTER(PdqnArgsT), _vp]
+    lib.rb200_c51_head.argtypes = [C.POINTER(C51ArgsT), _vp]
     lib.rb200_replay_add_device.argtypes = [C.POINTER(AddArgsT), _vp]
     lib.rb200_sumtree_set_device.argtypes = [_vp, C.c_int32, _vp, _vp, C.c_int32, _vp, _vp, _vp]
     lib.rb200_per_draw_indices.argtypes = [C.POINTER(PerDrawArgsT), _vp]

@@ -146,3 +146,36 @@ class ModelFeatureConfig:
     @property
     def only_dense(self):
         return True
+
+
+@dataclass
+class ParametricDqnInput(BaseInput):
+    """core/types.py:867-897: actions are feature vectors; the possible (next) actions of a row
+    are tiled along the batch dimension -- (batch_size * max_num_action, action_dim)."""
+    action: FeatureData = None
+    next_action: FeatureData = None
+    possible_actions: FeatureData = None
+    possible_actions_mask: torch.Tensor = None
+    possible_next_actions: FeatureData = None
+    possible_next_actions_mask: torch.Tensor = None
+    extras: Optional[ExtraData] = None
+    weight: Optional[torch.Tensor] = None
+
+    @classmethod
+    def from_dict(cls, batch):
+        return cls(
+            state=FeatureData(batch["state_features"]),
+            action=FeatureData(batch["action"]),
+            next_state=FeatureData(batch["next_state_features"]),
+            next_action=FeatureData(batch["next_action"]),
+            possible_actions=FeatureData(batch["possible_actions"]),
+            possible_actions_mask=batch["possible_actions_mask"],
+            possible_next_actions=FeatureData(batch["possible_next_actions"]),
+            possible_next_actions_mask=batch["possible_next_actions_mask"],
+            reward=batch["reward"],
+            not_terminal=batch["not_terminal"],
+            time_diff=batch.get("time_diff"),
+            step=batch.get("step"),
+            extras=batch.get("extras"),
+            weight=batch.get("weight"),
+        )

@@ -66,6 +66,8 @@ extern "C" int64_t rb200_abi_sizeof(const char* type_name) {
   RB200_SZ(rb200_sample_args_t);
   RB200_SZ(rb200_replay_dev_t);
   RB200_SZ(rb200_cpe_args_t);
+  RB200_SZ(rb200_pdqn_args_t);
+  RB200_SZ(rb200_c51_args_t);
   RB200_SZ(rb200_add_args_t);
   RB200_SZ(rb200_per_draw_args_t);
 #undef RB200_SZ

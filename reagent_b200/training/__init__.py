@@ -1,5 +1,7 @@
+from .c51_trainer import C51Trainer  # noqa: F401
 from .dqn_trainer import BCQConfig, DQNTrainer  # noqa: F401
 from .loop import run_update  # noqa: F401
+from .parametric_dqn_trainer import ParametricDQNTrainer  # noqa: F401
 from .qrdqn_trainer import QRDQNTrainer  # noqa: F401
 from .reagent_lightning_module import ReAgentLightningModule  # noqa: F401
 from .sac_trainer import SACTrainer  # noqa: F401

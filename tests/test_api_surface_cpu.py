@@ -170,7 +170,8 @@ def test_ctypes_mirrors_match_the_library_struct_sizes():
                "rb200_feature_col_t": _lib.FeatureColT, "rb200_dqn_args_t": _lib.DqnArgsT,
                "rb200_qrdqn_args_t": _lib.QrdqnArgsT, "rb200_ac_args_t": _lib.AcArgsT,
                "rb200_adam_args_t": _lib.AdamArgsT, "rb200_gather_spec_t": _lib.GatherSpecT,
-               "rb200_sample_args_t": _lib.SampleArgsT, "rb200_replay_dev_t": _lib.ReplayDevT, "rb200_cpe_args_t": _lib.CpeArgsT,
+               "rb200_sample_args_t": _lib.SampleArgsT, "rb200_replay_dev_t": _lib.ReplayDevT, "rb200_cpe_args_t": _lib.CpeArgsT, "rb200_pdqn_args_t": _lib.PdqnArgsT,
+               "rb200_c51_args_t": _lib.C51ArgsT,
                "rb200_add_args_t": _lib.AddArgsT, "rb200_per_draw_args_t": _lib.PerDrawArgsT}
     lib = _lib.lib()
     for name, mirror in mirrors.items():

@@ -304,3 +304,68 @@ def test_dqn_cpe_oracle_matches_reference(name):
         for i, (w, b) in enumerate(G.net_pairs(arrays, prefix)):
             assert G.rel_err(ps[2 * i], w) < 1e-6, (prefix, i)
             assert G.rel_err(ps[2 * i + 1], b) < 1e-6, (prefix, i)
+
+
+PDQN_CASES = ["pdqn_double_mse", "pdqn_sarsa_huber_reward", "pdqn_single_multistep"]
+C51_CASES = ["c51_double", "c51_single_masked_boost", "c51_sarsa_multistep"]
+
+
+@pytest.mark.parametrize("name", PDQN_CASES)
+def test_pdqn_oracle_matches_reference(name):
+    arrays, meta = G.load(name)
+    acts = meta["acts"] + ["linear"]
+    q = G.oracle_net(arrays, "q0", acts, requires_grad=True)
+    qt = G.oracle_net(arrays, "qt0", acts)
+    rn = G.oracle_net(arrays, "r0", acts, requires_grad=True) if meta["with_reward_net"] else None
+    batch = G.batch_tensors(arrays)
+    adam = O.AdamState(O.net_params(q), lr=meta["lr"])
+    adam_r = O.AdamState(O.net_params(rn), lr=meta["lr"]) if rn is not None else None
+    kw = dict(double_q=meta["double_q"], maxq=meta["maxq"], loss=meta["loss"], reward_net=rn, adam_r=adam_r,
+              discount_src=batch["step"] if meta["multi_steps"] is not None else None)
+    for it in range(meta["n_updates"]):
+        td, rl, grads = O.pdqn_update(q, qt, adam, batch, gamma=meta["gamma"], tau=meta["tau"], **kw)
+        assert abs(td - arrays["losses"][it][0]) <= 1e-6 * max(1.0, abs(arrays["losses"][it][0]))
+        if rn is not None:
+            assert abs(rl - arrays["losses"][it][1]) <= 1e-6 * max(1.0, abs(arrays["losses"][it][1]))
+        if it == 0:
+            for i, g in enumerate(grads):
+                assert G.rel_err(g, arrays[f"grad0.{i}"]) < 1e-6
+    nets = [(q, "qN"), (qt, "qtN")] + ([(rn, "rN")] if rn is not None else [])
+    for net, prefix in nets:
+        ps = O.net_params(net)
+        for i, (w, b) in enumerate(G.net_pairs(arrays, prefix)):
+            assert G.rel_err(ps[2 * i], w) < 1e-6 and G.rel_err(ps[2 * i + 1], b) < 1e-6, (prefix, i)
+
+
+def _c51_kwargs(meta, batch):
+    kw = dict(num_atoms=meta["N"], qmin=meta["qmin"], qmax=meta["qmax"], double_q=meta["double_q"],
+              maxq=meta["maxq"])
+    if meta["multi_steps"] is not None:
+        kw["discount_src"] = batch["step"]
+    if meta["boost"]:
+        rb = torch.zeros(1, meta["A"])
+        for k, v in meta["boost"].items():
+            rb[0, int(k)] = v
+        kw["reward_boost"] = rb
+    return kw
+
+
+@pytest.mark.parametrize("name", C51_CASES)
+def test_c51_oracle_matches_reference(name):
+    arrays, meta = G.load(name)
+    acts = meta["acts"] + ["linear"]
+    q = G.oracle_net(arrays, "q0", acts, requires_grad=True)
+    qt = G.oracle_net(arrays, "qt0", acts)
+    batch = G.batch_tensors(arrays)
+    adam = O.AdamState(O.net_params(q), lr=meta["lr"])
+    kw = _c51_kwargs(meta, batch)
+    for it in range(meta["n_updates"]):
+        loss, grads = O.c51_update(q, qt, adam, batch, gamma=meta["gamma"], tau=meta["tau"], **kw)
+        assert abs(loss - arrays["losses"][it]) <= 1e-6 * max(1.0, abs(arrays["losses"][it]))
+        if it == 0:
+            for i, g in enumerate(grads):
+                assert G.rel_err(g, arrays[f"grad0.{i}"]) < 1e-6
+    for net, prefix in ((q, "qN"), (qt, "qtN")):
+        ps = O.net_params(net)
+        for i, (w, b) in enumerate(G.net_pairs(arrays, prefix)):
+            assert G.rel_err(ps[2 * i], w) < 1e-6 and G.rel_err(ps[2 * i + 1], b) < 1e-6, (prefix, i)
