@@ -270,11 +270,19 @@ __global__ void __launch_bounds__(256) adam_soft_kernel(const AdamDev d) {
     }
     __syncthreads();
     const size_t fslot = ((size_t)par * W) * a.dp_max_blocks + blockIdx.x;
+    if (threadIdx.x == 0) {
+      // ONE system-scope fence orders every push of this block (made visible to this thread by
+      // the barrier) before the flags; the W-1 flag stores themselves are then relaxed and
+      // posted back to back (a release store per peer would pay the fence W-1 times)
+      __threadfence_system();
+      for (int r = 0; r < W; ++r) {
+        if (r == a.dp_rank) continue;
+        uint32_t* f = a.dp_flags[r] + fslot + (size_t)a.dp_rank * a.dp_max_blocks;
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;\n" ::"l"(f), "r"((uint32_t)t) : "memory");
+      }
+    }
     if ((int)threadIdx.x < W && (int)threadIdx.x != a.dp_rank) {
-      __threadfence_system();  // this block's pushes (ordered by the barrier) before the flag
-      uint32_t* f = a.dp_flags[threadIdx.x] + fslot + (size_t)a.dp_rank * a.dp_max_blocks;
-      asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(f), "r"((uint32_t)t) : "memory");
-      // and wait for that peer's push of the same slice (it never waits before pushing)
+      // wait for that peer's push of the same slice (it never waits before pushing)
       const uint32_t* w = a.dp_flags[a.dp_rank] + fslot + (size_t)threadIdx.x * a.dp_max_blocks;
       unsigned long long t0 = 0, now = 0;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
