@@ -62,20 +62,21 @@ print("tc fwd only us", timeit(lambda i: _lib.lib().rb200_dqn_td_step_tc(qd, qtd
 # ---- timeline of block 0 (clock64 stamps) ----
 import ctypes
 a.do_backward = 1
-dbg = torch.zeros(32 * 8 + 4 * 4096, dtype=torch.int64, device=dev)
+dbg = torch.zeros(32 * 8 + 4 * 4096 + 32 * 8, dtype=torch.int64, device=dev)
 _lib.lib().rb200_debug_set_tc_timeline(ctypes.c_void_p(dbg.data_ptr()))
 for _ in range(3):
     _lib.lib().rb200_dqn_td_step_tc(qd, qtd, a, wsc, pack.data_ptr(), pack.numel(), 0, st)
 torch.cuda.synchronize()
 _lib.lib().rb200_debug_set_tc_timeline(ctypes.c_void_p(0))
 d = dbg.cpu()[:256].view(32, 8)
-blk = dbg.cpu()[256:].view(-1, 4)[: (B + 31) // 32]
+blk = dbg.cpu()[256:256 + 4 * 4096].view(-1, 4)[: (B + 31) // 32]
+fine = dbg.cpu()[256 + 4 * 4096:].view(32, 8)
 t0 = int(d[0, 0])
 print("step  op_ready  issue_end  mma_wait_afull  epi_start  epi_end  arrive   (cycles from first op_ready); loader waits: full / adone")
 for s_ in range(32):
     if int(d[s_, 0]) == 0: break
     r = d[s_]
-    print(f"{s_:3d} {int(r[0])-t0:9d} {int(r[1])-t0:9d} {int(r[2]):9d} {int(r[3])-t0:9d} {int(r[4])-t0:9d} {int(r[5])-t0 if int(r[5]) else 0:9d}  ld_wait_full {int(r[6]):6d} ld_wait_adone {int(r[7]):6d}")
+    print(f"{s_:3d} {int(r[0])-t0:9d} {int(r[1])-t0:9d} {int(r[2]):9d} {int(r[3])-t0:9d} {int(r[4])-t0:9d} {int(r[5])-t0 if int(r[5]) else 0:9d}  ld_wait_full {int(r[6]):6d} ld_wait_adone {int(r[7]):6d} | mma: fence {int(fine[s_,0])} issue {int(fine[s_,1])} commit {int(fine[s_,2])} | loader: lds+split {int(fine[s_,3])} st+arrive {int(fine[s_,4])}")
 if int(blk[0, 0]):
     st0 = int(blk[:, 0].min())
     print("per-block ns: start spread %d, setup %.0f avg, run avg %.0f max %.0f, last end %d" % (

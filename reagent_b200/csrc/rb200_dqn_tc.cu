@@ -48,13 +48,24 @@
 namespace rb200 {
 
 constexpr int kQR = 32;                                   // batch rows per CTA
-#ifndef RB200_QSTAGES
-#define RB200_QSTAGES 6
+// A ring stage (shared memory and tensor memory alike) holds kQSub consecutive 32-k chunk images
+// of one feature tile (they are contiguous in the image: the k-quad sequence simply continues).
+// Every mbarrier wait costs 100-150 cycles even when it passes at once, and each agent of the
+// weight stream is a sequential loop with two waits per stage, so the stage is the unit that
+// amortises them: 64 k per stage halves the synchronisation cost per MMA.
+#ifndef RB200_QSUB
+#define RB200_QSUB 2
 #endif
-constexpr int kQStages = RB200_QSTAGES;                   // shared-memory ring depth (raw fp32 chunks)
-constexpr int kQStageBytes = (kQKC / 4) * kQFullLbo;      // one chunk image
-constexpr int kAStages = 4;                               // tensor-memory ring depth (split chunks)
-constexpr int kAStageCols = 2 * kQKC;                     // hi columns then lo columns of a chunk
+constexpr int kQSub = RB200_QSUB;
+#ifndef RB200_QSTAGES
+#define RB200_QSTAGES (6 / RB200_QSUB)
+#endif
+constexpr int kQStages = RB200_QSTAGES;                   // shared-memory ring depth (raw fp32 stages)
+constexpr int kQStageBytes = kQSub * (kQKC / 4) * kQFullLbo;  // kQSub chunk images
+constexpr int kAMaxStages = 7;                            // tensor-memory ring depth (split chunks), upper bound:
+                                                          // the plan uses every column the accumulators leave free
+constexpr int kASubCols = 2 * kQKC;                       // hi columns then lo columns of a chunk
+constexpr int kAStageCols = kQSub * kASubCols;
 // B operand (activations): per k quad 64 rows of 16 B -- rows 0-31 hold the hi parts of the 32
 // batch rows, rows 32-63 their lo parts -- plus 16 B of padding.  One N = 64 MMA against W_hi
 // then yields W_hi.X_hi in accumulator columns 0-31 and W_hi.X_lo in columns 32-63; a second
@@ -63,13 +74,26 @@ constexpr int kAStageCols = 2 * kQKC;                     // hi columns then lo 
 constexpr int kQLboB = 64 * 16 + 16;
 constexpr int kQLoOff = 32 * 4;                           // floats from a hi element to its lo
 constexpr int kQEpiThreads = 256;
-constexpr int kQLoaderWarps = 4;                          // one per TMEM lane quadrant
+#ifndef RB200_QGROUPS
+#define RB200_QGROUPS 1
+#endif
+// Loader warps: kQLoaderGroups groups of four (one warp per TMEM lane quadrant).  Chunk i of the
+// weight stream belongs to group i % kQLoaderGroups, so consecutive chunks are converted by
+// different warps concurrently: one warp needs ~350 cycles per chunk (wait, 8 loads, ~100 ALU
+// instructions, two tensor-memory stores and their completion), the MMAs of a chunk 192.
+constexpr int kQLoaderGroups = RB200_QGROUPS;
+constexpr int kQLoaderWarps = 4 * kQLoaderGroups;
+// registers per thread: the register file is 16 K per SM sub-partition and the warps of a CTA
+// are dealt round-robin to the four sub-partitions
+constexpr int kQRegs = kQLoaderGroups >= 3 ? 80 : (kQLoaderGroups == 2 ? 96 : 128);
 constexpr int kQThreads = kQEpiThreads + 64 + 32 * kQLoaderWarps;  // + producer + MMA + loaders
 constexpr int kQMaxTiles = 4;                             // accumulators: 4 feature tiles x 64 columns
 constexpr int kQAccCols = kQMaxTiles * 64;
 constexpr int kQTmemCols = 512;                           // accumulators + the weight ring
-static_assert(kQAccCols + kAStages * kAStageCols <= kQTmemCols, "tensor memory budget");
-static_assert(kQKC == 32 || kQKC == 16, "loader warps move 16- or 32-k chunks");
+static_assert(kQAccCols + 2 * kAStageCols <= kQTmemCols, "tensor memory budget");
+static_assert(((10 + kQLoaderWarps + 3) / 4) * 32 * kQRegs <= 16384, "register file budget per sub-partition");
+static_assert(kQKC == 32, "loader warps move 32-k chunks");
+static_assert(kQStages % kQLoaderGroups == 0, "a shared-memory ring stage belongs to one loader group");
 constexpr int kQMaxSteps = 4 * kMaxLayers;
 constexpr int kQMaxSmem = 232448;
 #ifndef RB200_TC_TIMELINE
@@ -92,7 +116,10 @@ struct QDev {
   int nsteps, last_fwd_step;
   int buf_off[3];  // operand buffers (bytes from the smem base); [2] holds dZ of the last layer
   int q_off, ldq, lin_off, bar_off;
-  int dbg_mode;     // profiling only: 1 skip the N=32 MMAs, 2 skip the N=64 MMAs, 3 skip both
+  int acc_cols, a_stages;  // tensor memory: accumulator columns, then a_stages weight stages
+  int need_zero;    // some layer width is not a multiple of 8: clear the operand buffers first
+  int dbg_mode;     // profiling only (bits): 1 skip the N=32 MMAs, 2 skip the N=64 MMAs, 4 no ring reads,
+                    // 8 no bulk-copy traffic, 16 no tensor-memory stores, 32 no epilogue stores
   long long* dbg;  // optional timeline of block 0: [step][8] clock64 stamps (profiling builds)
   QStep steps[kQMaxSteps];
 };
@@ -228,10 +255,9 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
-// 128 registers x 448 threads (the register file is 16 K per SM sub-partition: 4 warps x 32 x 128) and ~214 KB of shared memory leave room on the SM for one CTA
-// of the replay-sample kernel (48 registers x 256 threads, < 10 KB), so the sampler of the next
-// update can run on a second stream underneath this kernel instead of delaying its CTAs.
-__global__ void __maxnreg__(128)
+// Register cap: threads x registers must fit the 64 K register file (kQRegs; the kernel needs
+// 76-107 depending on the cap, no spills).
+__global__ void __maxnreg__(kQRegs)
 dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -243,8 +269,11 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
   auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
   if (kTimeline && p.dbg && tid == 0) p.dbg[kQMaxSteps * 8 + blockIdx.x * 4 + 0] = gtime();
 
-  // operand padding (k up to the next multiple of 8, rows past the batch) must be finite
-  {
+  // operand padding (k up to the next multiple of 8) must be finite.  With every layer width a
+  // multiple of 8 there is no padding: all operand quads, all 64 B-operand rows (rows past the
+  // batch are stored as zeros) and the loss inputs are fully written before they are read, and
+  // the ~115 KB clear (about 1 us per CTA) is skipped.
+  if (p.need_zero) {
     unsigned nbytes;
     asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(nbytes));
     // (the weight ring is fully overwritten by the bulk copies; rows a partial tile over-reads
@@ -263,17 +292,18 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + p.bar_off);
   uint64_t* sfree = full + kQStages;
   uint64_t* afull = sfree + kQStages;
-  uint64_t* adone = afull + kAStages;
-  uint64_t* dready = adone + kAStages;  // one per accumulator tile (see the epilogue)
+  uint64_t* adone = afull + kAMaxStages;
+  uint64_t* dready = adone + kAMaxStages;  // one per accumulator tile (see the epilogue)
   uint64_t* opready = dready + kQMaxTiles;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(opready + 1);
   const int ldq = p.ldq;
 
   if (tid == 0) {
-    for (int s = 0; s < kQStages; ++s) { mbar_init(full + s, 1); mbar_init(sfree + s, kQLoaderWarps); }
-    for (int t = 0; t < kAStages; ++t) { mbar_init(afull + t, kQLoaderWarps); mbar_init(adone + t, 1); }
+    // a chunk is handled by the four warps of ONE loader group
+    for (int s = 0; s < kQStages; ++s) { mbar_init(full + s, 1); mbar_init(sfree + s, 4); }
+    for (int t = 0; t < kAMaxStages; ++t) { mbar_init(afull + t, 4); mbar_init(adone + t, 1); }
     for (int t = 0; t < kQMaxTiles; ++t) mbar_init(dready + t, 1);
-    mbar_init(opready, kQEpiThreads);
+    mbar_init(opready, kQEpiThreads / 32);  // one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
@@ -307,12 +337,14 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
         const int klast = st.K - kQKC * (kch - 1);
         const uint32_t last_bytes = (uint32_t)(round_up8(klast) / 4) * lbo;
         const unsigned char* src = p.pack + st.pack_off + (size_t)t * tile_stride;
-        for (int c = 0; c < kch; ++c) {
-          const uint32_t bytes = (c == kch - 1) ? last_bytes : full_bytes;
+        for (int c = 0; c < kch; c += kQSub) {
+          const int nsub = kch - c < kQSub ? kch - c : kQSub;
+          const uint32_t bytes = (uint32_t)(nsub - 1) * full_bytes + ((c + nsub == kch) ? last_bytes : full_bytes);
+          const uint32_t cbytes = (kTimeline && (p.dbg_mode & 8)) ? 16u : bytes;  // profiling: no copy traffic
           mbar_wait(sfree + stage, par);
           if (leader) {
-            mbar_expect_tx(full + stage, bytes);
-            bulk_g2s(ring + stage * kQStageBytes, src, bytes, full + stage);
+            mbar_expect_tx(full + stage, cbytes);
+            bulk_g2s(ring + stage * kQStageBytes, src, cbytes, full + stage);
           }
           src += bytes;
           if (++stage == kQStages) { stage = 0; par ^= 1u; }
@@ -334,40 +366,53 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
       const int mt = ceil_div(st.N, 128), kch = ceil_div(st.K, kQKC);
       mbar_wait(opready, (uint32_t)s & 1u);
       tc_fence_after();
-      long long wafull = 0;
+      long long wafull = 0, tfence = 0, tissue = 0, tcommit = 0;
       if (kTimeline && p.dbg && blockIdx.x == 0 && leader) p.dbg[s * 8 + 0] = clock64();
       const uint32_t b0 = ((smem_u32(smem_raw + p.buf_off[st.in_buf]) >> 4) & 0x3fffu) |
                           ((uint32_t)(kQLboB >> 4) << 16);
       for (int t = 0; t < mt; ++t) {
         const uint32_t d = tmem + (uint32_t)(t * 64);
         uint32_t bdesc = b0;  // advances by two k quads per MMA k step
-        for (int c = 0; c < kch; ++c) {
-          const int kl = st.K - kQKC * c;
-          const int ksteps = round_up8(kl < kQKC ? kl : kQKC) / 8;
+        for (int c = 0; c < kch; c += kQSub) {
+          const int nsub = kch - c < kQSub ? kch - c : kQSub;
           const long long w0 = (kTimeline && p.dbg) ? clock64() : 0;
           mbar_wait(afull + ts, tpar);
-          if (kTimeline && p.dbg) wafull += clock64() - w0;
+          const long long w1 = (kTimeline && p.dbg) ? clock64() : 0;
+          if (kTimeline && p.dbg) wafull += w1 - w0;
           tc_fence_after();
+          const long long w2 = (kTimeline && p.dbg) ? clock64() : 0;
+          if (kTimeline && p.dbg) tfence += w2 - w1;
           if (leader) {
-            uint32_t a_hi = tmem + (uint32_t)(kQAccCols + ts * kAStageCols);
             uint32_t bd = bdesc;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              if (!kTimeline || !(p.dbg_mode & 2))
-                umma_tf32_ts(d, a_hi, desc_hi | bd, idesc64, (c > 0 || ks > 0) ? 1u : 0u);
-              if (!kTimeline || !(p.dbg_mode & 1))
-                umma_tf32_ts(d, a_hi + kQKC, desc_hi | bd, idesc32, 1u);
-              a_hi += 8;
-              bd += (2u * kQLboB) >> 4;
+            for (int j = 0; j < nsub; ++j) {
+              const int kl = st.K - kQKC * (c + j);
+              const int ksteps = round_up8(kl < kQKC ? kl : kQKC) / 8;
+              uint32_t a_hi = tmem + (uint32_t)(p.acc_cols + ts * kAStageCols + j * kASubCols);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                if (!kTimeline || !(p.dbg_mode & 2))
+                  umma_tf32_ts(d, a_hi, desc_hi | bd, idesc64, (c + j > 0 || ks > 0) ? 1u : 0u);
+                if (!kTimeline || !(p.dbg_mode & 1))
+                  umma_tf32_ts(d, a_hi + kQKC, desc_hi | bd, idesc32, 1u);
+                a_hi += 8;
+                bd += (2u * kQLboB) >> 4;
+              }
             }
+            const long long w3 = (kTimeline && p.dbg) ? clock64() : 0;
             umma_commit(adone + ts);  // this TMEM stage may be refilled once the MMAs retired
+            if (kTimeline && p.dbg) { const long long w4 = clock64(); tissue += w3 - w2; tcommit += w4 - w3; }
           }
-          bdesc += (uint32_t)(kQKC / 4) * (kQLboB >> 4);
-          if (++ts == kAStages) { ts = 0; tpar ^= 1u; }
+          bdesc += (uint32_t)nsub * (uint32_t)(kQKC / 4) * (kQLboB >> 4);
+          if (++ts == p.a_stages) { ts = 0; tpar ^= 1u; }
         }
         // one accumulator tile complete: its epilogue runs while the next tile's MMAs issue
         if (leader) umma_commit(dready + t);
       }
-      if (kTimeline && p.dbg && blockIdx.x == 0 && leader) { p.dbg[s * 8 + 1] = clock64(); p.dbg[s * 8 + 2] = wafull; }
+      if (kTimeline && p.dbg && blockIdx.x == 0 && leader) {
+        p.dbg[s * 8 + 1] = clock64();
+        p.dbg[s * 8 + 2] = wafull;
+        long long* fine = p.dbg + kQMaxSteps * 8 + 4 * 4096 + s * 8;
+        fine[0] = tfence; fine[1] = tissue; fine[2] = tcommit;
+      }
       __syncwarp();
     }
   } else if (role >= kQEpiThreads / 32 + 2) {
@@ -375,58 +420,82 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
     // warp (10 + j) may touch TMEM lanes [32*((10+j)%4), +32): the four loader warps cover the
     // four lane quadrants; lane i of a warp owns weight row 32*quadrant + i of the tile.
     const int quadrant = warp & 3;
+    const int group = (warp - (kQEpiThreads / 32 + 2)) >> 2;
+    int turn = 0;  // group whose chunk comes next; every warp walks the whole chunk sequence
     const int r = quadrant * 32 + lane;
     int ss = 0, ts = 0;
     uint32_t spar = 0, tpar = 1;  // TMEM stages start free (parity of the previous use)
     for (int s = 0; s < p.nsteps; ++s) {
       const QStep st = p.steps[s];
       const int mt = ceil_div(st.N, 128), kch = ceil_div(st.K, kQKC);
-      long long lwfull = 0, lwdone = 0;
+      long long lwfull = 0, lwdone = 0, lsplit = 0, lstore = 0;
       for (int t = 0; t < mt; ++t) {
         const int rows = st.N - 128 * t;
         const int rows8 = round_up8(rows < 128 ? rows : 128);
         const uint32_t lbo = (uint32_t)(rows8 * 16 + 16);
-        for (int c = 0; c < kch; ++c) {
-          const int kl = st.K - kQKC * c;
-          const int nq = round_up8(kl < kQKC ? kl : kQKC) / 4;
+        for (int c = 0; c < kch; c += kQSub) {
+          const int nsub = kch - c < kQSub ? kch - c : kQSub;
+          const bool mine = turn == group;
+          if (++turn == kQLoaderGroups) turn = 0;
+          if (!mine) {
+            if (++ss == kQStages) { ss = 0; spar ^= 1u; }
+            if (++ts == p.a_stages) { ts = 0; tpar ^= 1u; }
+            continue;
+          }
           const long long l0 = (kTimeline && p.dbg) ? clock64() : 0;
           mbar_wait(full + ss, spar);
-          if (kTimeline && p.dbg) lwfull += clock64() - l0;
-          float hi[32], lo[32];
-          const unsigned char* src = ring + ss * kQStageBytes + r * 16;
-#pragma unroll
-          for (int qd = 0; qd < kQKC / 4; ++qd) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (qd < nq && r < rows8) v = *reinterpret_cast<const float4*>(src + qd * lbo);
-            float4 h, l;
-            split4(v, h, l);
-            hi[4 * qd + 0] = h.x; hi[4 * qd + 1] = h.y; hi[4 * qd + 2] = h.z; hi[4 * qd + 3] = h.w;
-            lo[4 * qd + 0] = l.x; lo[4 * qd + 1] = l.y; lo[4 * qd + 2] = l.z; lo[4 * qd + 3] = l.w;
-          }
-#pragma unroll
-          for (int i = kQKC; i < 32; ++i) { hi[i] = 0.f; lo[i] = 0.f; }
-          // the values are in registers: the shared-memory stage can be refilled
-          __syncwarp();
-          if (lane == 0) mbar_arrive(sfree + ss);
-          const long long l1 = (kTimeline && p.dbg) ? clock64() : 0;
-          mbar_wait(adone + ts, tpar);  // the MMAs that read this TMEM stage have retired
-          if (kTimeline && p.dbg) lwdone += clock64() - l1;
-          tc_fence_after();
+          const long long l0b = (kTimeline && p.dbg) ? clock64() : 0;
+          if (kTimeline && p.dbg) lwfull += l0b - l0;
           const uint32_t ta = tmem + ((uint32_t)(quadrant * 32) << 16) +
-                              (uint32_t)(kQAccCols + ts * kAStageCols);
-          if (kQKC == 32) { tmem_st32(ta, hi); tmem_st32(ta + kQKC, lo); }
-          else { tmem_st16(ta, hi); tmem_st16(ta + kQKC, lo); }
+                              (uint32_t)(p.acc_cols + ts * kAStageCols);
+#pragma unroll 1
+          for (int j = 0; j < nsub; ++j) {
+            const int kl = st.K - kQKC * (c + j);
+            const int nq = round_up8(kl < kQKC ? kl : kQKC) / 4;
+            float hi[32], lo[32];
+            const unsigned char* src = ring + ss * kQStageBytes + (uint32_t)j * (kQKC / 4) * lbo + r * 16;
+#pragma unroll
+            for (int qd = 0; qd < kQKC / 4; ++qd) {
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (kTimeline && (p.dbg_mode & 4)) v = make_float4(1.f, 2.f, 3.f, 4.f);  // profiling: no ring reads
+              else if (qd < nq && r < rows8) v = *reinterpret_cast<const float4*>(src + qd * lbo);
+              float4 h, l;
+              split4(v, h, l);
+              hi[4 * qd + 0] = h.x; hi[4 * qd + 1] = h.y; hi[4 * qd + 2] = h.z; hi[4 * qd + 3] = h.w;
+              lo[4 * qd + 0] = l.x; lo[4 * qd + 1] = l.y; lo[4 * qd + 2] = l.z; lo[4 * qd + 3] = l.w;
+            }
+            if (j == nsub - 1) {
+              // the stage's values are in registers: the shared-memory stage can be refilled
+              __syncwarp();
+              if (lane == 0) mbar_arrive(sfree + ss);
+            }
+            if (j == 0) {
+              const long long l1 = (kTimeline && p.dbg) ? clock64() : 0;
+              if (kTimeline && p.dbg) lsplit += l1 - l0b;
+              mbar_wait(adone + ts, tpar);  // the MMAs that read this TMEM stage have retired
+              if (kTimeline && p.dbg) lwdone += clock64() - l1;
+              tc_fence_after();
+            }
+            if (!kTimeline || !(p.dbg_mode & 16)) {  // (profiling: no tensor-memory stores)
+              tmem_st32(ta + j * kASubCols, hi);
+              tmem_st32(ta + j * kASubCols + kQKC, lo);
+            }
+          }
+          const long long l2 = (kTimeline && p.dbg) ? clock64() : 0;
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(afull + ts);
+          if (kTimeline && p.dbg) lstore += clock64() - l2;
           if (++ss == kQStages) { ss = 0; spar ^= 1u; }
-          if (++ts == kAStages) { ts = 0; tpar ^= 1u; }
+          if (++ts == p.a_stages) { ts = 0; tpar ^= 1u; }
         }
       }
-      if (kTimeline && p.dbg && blockIdx.x == 0 && quadrant == 0 && lane == 0) {
+      if (kTimeline && p.dbg && blockIdx.x == 0 && quadrant == 0 && group == 0 && lane == 0) {
         p.dbg[s * 8 + 6] = lwfull;
         p.dbg[s * 8 + 7] = lwdone;
+        long long* fine = p.dbg + kQMaxSteps * 8 + 4 * 4096 + s * 8;
+        fine[3] = lsplit; fine[4] = lstore;
       }
     }
   } else {
@@ -576,6 +645,7 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
           gdst = to_global ? p.ws.hidden[l] : nullptr;
         }
         if (!valid) continue;
+        if (kTimeline && (p.dbg_mode & 32)) { to_operand = false; to_global = false; }  // profiling: no epilogue stores
         if (st.kind == kStepLast) {
           float* qd = qarr + (st.qdst * kQR + h16) * ldq + n;
 #pragma unroll
@@ -680,8 +750,14 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
 
     auto x_src = [&](int lx) { return lx == 1 ? a.state : a.next_state; };
     if (p.steps[0].load_x) { x_fetch(x_src(p.steps[0].load_x)); x_store(x_src(p.steps[0].load_x)); }
-    fence_proxy_async_smem();
-    mbar_arrive(opready);
+    // hand-over: every thread makes its operand stores visible to the async proxy, the warp
+    // converges, ONE lane arrives (8 arrivals per hand-over instead of 256 serialised ones)
+    auto operand_ready = [&]() {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(opready);
+    };
+    operand_ready();
     load_loss_inputs();
     for (int s = 0; s < p.nsteps; ++s) {
       const QStep st = p.steps[s];
@@ -697,8 +773,7 @@ dqn_td_tc_kernel(const Mlp q, const Mlp qt, const QDev p) {
       }
       if (s + 1 < p.nsteps) {
         if (lx) x_store(x_src(lx));
-        fence_proxy_async_smem();
-        mbar_arrive(opready);
+        operand_ready();
         if (kTimeline && p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 5] = clock64();
       }
     }
@@ -826,6 +901,21 @@ static QPlan make_plan(const rb200_mlp_t* qn, const rb200_mlp_t* qtn, int double
     }
   }
   pl.dev.nsteps = ns;
+  {
+    // tensor memory: accumulators for the widest layer, every other column is weight ring
+    int tiles = 1;
+    for (int l = 1; l <= L; ++l) tiles = tiles > ceil_div(qn->dims[l], 128) ? tiles : ceil_div(qn->dims[l], 128);
+    pl.dev.acc_cols = 64 * tiles;
+    int st = (kQTmemCols - pl.dev.acc_cols) / kAStageCols;
+    st = st < kAMaxStages ? st : kAMaxStages;
+    // a ring stage must belong to ONE loader group (tests/test_tc_protocol_model.py): depth is a
+    // multiple of the group count
+    pl.dev.a_stages = st / kQLoaderGroups * kQLoaderGroups;
+    if (pl.dev.a_stages < 2) return pl;
+  }
+  pl.dev.need_zero = 0;
+  for (int l = 0; l <= L; ++l)
+    if (qn->dims[l] % 8 != 0) pl.dev.need_zero = 1;
 
   // shared memory
   int maxd[3] = {8, 8, qn->dims[L]};
@@ -843,7 +933,7 @@ static QPlan make_plan(const rb200_mlp_t* qn, const rb200_mlp_t* qtn, int double
   o += ((size_t)2 * kQR * qn->dims[L] + 4 * kQR + 8) * sizeof(float);
   o = (o + 15) & ~(size_t)15;
   pl.dev.bar_off = (int)o;
-  o += (2 * kQStages + 2 * kAStages + kQMaxTiles + 1) * sizeof(uint64_t) + 16;
+  o += (2 * kQStages + 2 * kAMaxStages + kQMaxTiles + 1) * sizeof(uint64_t) + 16;
   pl.smem_bytes = (o + 15) & ~(size_t)15;
   pl.ok = pl.smem_bytes <= (size_t)kQMaxSmem;
   return pl;

@@ -1,8 +1,10 @@
 """Model check of the mbarrier protocol of the tcgen05 TD kernel (reagent_b200/csrc/rb200_dqn_tc.cu).
 
 The kernel's step loop is synchronised only by mbarriers that are waited on by PARITY:
-  full[s] / sfree[s]  shared-memory weight ring (producer warp <-> 4 loader warps)
-  afull[t] / adone[t] tensor-memory weight ring (4 loader warps <-> MMA warp)
+  full[s] / sfree[s]  shared-memory weight ring (producer warp <-> the 4 loader warps of ONE group)
+  afull[t] / adone[t] tensor-memory weight ring (those 4 loader warps <-> MMA warp)
+Chunk i of the weight stream belongs to loader group i % GROUPS (groups convert consecutive
+chunks concurrently); every loader warp tracks the stage / parity sequence of ALL chunks.
   dready[t]           accumulator tile t complete (MMA warp -> 8 epilogue warps), one per tile
   opready             next B operand in shared memory (epilogue threads -> MMA warp)
 A parity wait cannot tell "the phase I want" from "two phases later", so the protocol is only
@@ -18,9 +20,7 @@ import random
 
 import pytest
 
-STAGES = 6   # kQStages (shared memory)
-ASTAGES = 4  # kAStages (tensor memory)
-LOADERS = 4  # loader warps: one arrival each on sfree / afull
+LOADERS = 4  # loader warps of one group: one arrival each on sfree / afull
 
 
 class MBar:
@@ -47,11 +47,18 @@ def wait_ok(bar, intended):
         # the waiter is two (or more) completions late: a parity wait would now block forever
         # (or, one later, pass for the wrong phase)
         raise Hazard(f"aliasing: intended completion {intended}, barrier at {bar.completed}")
+    if intended >= bar.completed + 2 and (bar.completed & 1) != parity:
+        # the waiter is two phases EARLY: the parity test passes on a completion that is two
+        # behind the one it wants
+        raise Hazard(f"early pass: intended completion {intended}, barrier at {bar.completed}")
     return (bar.completed & 1) != parity
 
 
-def simulate(steps, n_epi, rng, shared_dready=False, max_ticks=200000):
-    """steps: list of (tiles, chunks_per_tile).  Returns True when every agent finished."""
+def simulate(steps, n_epi, rng, shared_dready=False, max_ticks=400000, groups=1, astages=3, stages=3):
+    """steps: list of (tiles, chunks_per_tile); groups = kQLoaderGroups, astages = QDev.a_stages
+    (2..7, whatever the accumulators leave; a stage holds kQSub chunks).  Returns True when every agent finished."""
+    ASTAGES = astages
+    STAGES = stages
     full = [MBar(1) for _ in range(STAGES)]
     sfree = [MBar(LOADERS) for _ in range(STAGES)]
     afull = [MBar(LOADERS) for _ in range(ASTAGES)]
@@ -73,8 +80,10 @@ def simulate(steps, n_epi, rng, shared_dready=False, max_ticks=200000):
             n += 1
             yield
 
-    def loader():
+    def loader(group):
         for n in range(total_chunks):
+            if n % groups != group:
+                continue
             ss, suse = n % STAGES, n // STAGES
             ts, tuse = n % ASTAGES, n // ASTAGES
             while not wait_ok(full[ss], suse + 1):
@@ -90,6 +99,12 @@ def simulate(steps, n_epi, rng, shared_dready=False, max_ticks=200000):
             afull[ts].arrive()
             yield
 
+    commit_due = [0]  # tcgen05.commit completions happen in issue order
+
+    def commit_at(lo, hi):
+        commit_due[0] = max(commit_due[0], tick[0] + rng.randint(lo, hi))
+        return commit_due[0]
+
     def mma():
         n = 0
         for s, (tiles, chunks) in enumerate(steps):
@@ -100,12 +115,12 @@ def simulate(steps, n_epi, rng, shared_dready=False, max_ticks=200000):
                     ts, tuse = n % ASTAGES, n // ASTAGES
                     while not wait_ok(afull[ts], tuse + 1):
                         yield
-                    pending_events.append((tick[0] + rng.randint(1, 12), adone[ts].arrive))
+                    pending_events.append((commit_at(1, 12), adone[ts].arrive))
                     n += 1
                     yield
                 bar = dready[0 if shared_dready else t]
                 # tcgen05.commit tracks ALL earlier MMAs: completes after the last one above
-                pending_events.append((tick[0] + rng.randint(12, 20), bar.arrive))
+                pending_events.append((commit_at(1, 20), bar.arrive))
                 yield
 
     def epilogue(speed):
@@ -124,7 +139,7 @@ def simulate(steps, n_epi, rng, shared_dready=False, max_ticks=200000):
             yield
 
     tick = [0]
-    agents = ([producer(), mma()] + [loader() for _ in range(LOADERS)]
+    agents = ([producer(), mma()] + [loader(g) for g in range(groups) for _ in range(LOADERS)]
               + [epilogue(rng.choice([3, 10, 40])) for _ in range(n_epi)])
     alive = list(agents)
     while alive and tick[0] < max_ticks:
@@ -150,11 +165,49 @@ def test_protocol_makes_progress_and_never_aliases():
     rng = random.Random(1234)
     for trial in range(150):
         steps = _random_steps(rng)
-        assert simulate(steps, n_epi=rng.randint(1, 4), rng=rng), (trial, steps)
+        # the kernel requires both ring depths to be multiples of the number of loader groups, so
+        # that a ring stage is only ever used by ONE group: bulk copies may land out of order, and
+        # a group that could reach a stage two uses early would pass its parity wait on the wrong
+        # completion (see the tests below)
+        g = rng.randint(1, 3)
+        astages = g * rng.randint(1 if g > 1 else 2, 7 // g)
+        stages = g * rng.randint(1 if g > 1 else 2, 6 // g)
+        assert simulate(steps, n_epi=rng.randint(1, 4), rng=rng, groups=g, astages=astages,
+                        stages=stages), (trial, steps)
     # the shapes of BASELINE config 2: 3 passes x (2x4, 1x8, 1x4 chunks) + backward (1x1, 2x4)
     cfg2 = [(2, 4), (1, 8), (1, 4)] * 3 + [(1, 1), (2, 4)]
     for _ in range(20):
-        assert simulate(cfg2, n_epi=4, rng=rng)
+        assert simulate(cfg2, n_epi=4, rng=rng, groups=1, astages=3, stages=3)
+    # the same network in 64-k stages: (2x2, 1x4, 1x2) x 3 + (1x1, 2x2)
+    cfg2s = [(2, 2), (1, 4), (1, 2)] * 3 + [(1, 1), (2, 2)]
+    for _ in range(20):
+        assert simulate(cfg2s, n_epi=4, rng=rng, groups=1, astages=3, stages=3)
+
+
+def test_model_catches_more_loader_groups_than_ring_stages():
+    """With more loader groups than tensor-memory stages a group can reach a stage two uses
+    early, where a parity wait passes on the wrong completion."""
+    rng = random.Random(11)
+    caught = 0
+    for _ in range(40):
+        try:
+            simulate([(2, 6)] * 6, n_epi=2, rng=rng, groups=4, astages=2, stages=4, max_ticks=40000)
+        except Hazard:
+            caught += 1
+    assert caught > 0
+
+
+def test_model_catches_ring_stages_shared_between_loader_groups():
+    """Two loader groups on a 3-stage shared-memory ring: copies land out of order, one group
+    runs ahead onto a stage whose previous use (the other group's) has not landed yet."""
+    rng = random.Random(5)
+    caught = 0
+    for _ in range(60):
+        try:
+            simulate([(2, 6)] * 6, n_epi=2, rng=rng, groups=2, astages=4, stages=3, max_ticks=40000)
+        except Hazard:
+            caught += 1
+    assert caught > 0
 
 
 def test_model_catches_the_shared_accumulator_barrier_bug():
