@@ -318,6 +318,16 @@ int rb200_linear_forward_tc(const float* W, const float* b, int32_t act, int32_t
 int rb200_linear_backward_dx(const float* W, int32_t K, int32_t N, const float* dz,
                              const float* h_prev, int32_t act_prev, int32_t batch, float* out,
                              void* stream);
+/* tcgen05 implementation of rb200_linear_backward_dx for a wide layer (the contraction runs
+ * over the N out-features: split-K slices of the tensor-core GEMM, added in a fixed order).
+ * _scratch_bytes returns 0 when the shape is not taken by this path (N < 1024, batch < 256 or
+ * K / N not multiples of 4): call rb200_linear_backward_dx then.  Replaces the same autograd
+ * step (torch.nn.functional.linear backward w.r.t. input, reagent/training/qrdqn_trainer.py:
+ * 108-194 via reagent_lightning_module.py:108-133). */
+int64_t rb200_linear_backward_dx_tc_scratch_bytes(int32_t K, int32_t N, int32_t batch);
+int rb200_linear_backward_dx_tc(const float* W, int32_t K, int32_t N, const float* dz,
+                                const float* h_prev, int32_t act_prev, int32_t batch, float* out,
+                                void* scratch, int64_t scratch_bytes, void* stream);
 int rb200_mlp_backward(const rb200_mlp_t* net, const float* dz_last, int32_t batch,
                        const rb200_net_ws_t* ws, void* stream);
 int rb200_qrdqn_head(const rb200_qrdqn_args_t* args, void* stream);

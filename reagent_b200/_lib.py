@@ -254,6 +254,10 @@ def _declare(lib):
                                          C.c_int32, _vp, _vp]
     lib.rb200_linear_backward_dx.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32,
                                              C.c_int32, _vp, _vp]
+    lib.rb200_linear_backward_dx_tc_scratch_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    lib.rb200_linear_backward_dx_tc_scratch_bytes.restype = C.c_int64
+    lib.rb200_linear_backward_dx_tc.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32,
+                                                C.c_int32, _vp, _vp, C.c_int64, _vp]
     lib.rb200_mlp_backward.argtypes = [C.POINTER(MlpT), _vp, C.c_int32, C.POINTER(NetWsT), _vp]
     lib.rb200_qrdqn_head.argtypes = [C.POINTER(QrdqnArgsT), _vp]
     lib.rb200_preprocess.argtypes = [_vp, _vp, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _vp,

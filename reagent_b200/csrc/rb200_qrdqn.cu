@@ -128,9 +128,15 @@ __global__ void __launch_bounds__(256) qr_head_kernel(const QrDev d) {
   float* means = cq + N;     // [A]
   float* red = means + A;    // [256]
   __shared__ int s_best;
+  __shared__ float s_act[64], s_nact[64];  // action / next_action weights of this row (A <= 64 staged)
   const int b = blockIdx.x, tid = threadIdx.x;
   const size_t base = (size_t)b * A * N;
 
+  const bool staged = A <= 64;
+  if (staged && tid < A) {
+    s_act[tid] = a.action[(size_t)b * A + tid];
+    s_nact[tid] = (!a.maxq && a.next_action) ? a.next_action[(size_t)b * A + tid] : 0.f;
+  }
   // mean over atoms of the selection network (qrdqn_trainer.py:127-133)
   const float* sel = a.double_q ? a.q_next_online : a.q_next_target;
   for (int act = tid >> 5; act < A; act += 8) {
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(256) qr_head_kernel(const QrDev d) {
   float rew = a.reward[b];
   if (a.reward_boost) {
     float bs = 0.f;
-    for (int c = 0; c < A; ++c) bs += a.action[(size_t)b * A + c] * a.reward_boost[c];
+    for (int c = 0; c < A; ++c) bs += (staged ? s_act[c] : a.action[(size_t)b * A + c]) * a.reward_boost[c];
     rew += bs;
   }
   const float disc = a.discount_src ? powf(a.gamma, a.discount_src[b]) : a.gamma;
@@ -170,12 +176,12 @@ __global__ void __launch_bounds__(256) qr_head_kernel(const QrDev d) {
     } else {
       nq = 0.f;                                                         // SARSA (:139)
       for (int c = 0; c < A; ++c)
-        nq += a.q_next_target[base + (size_t)c * N + n] * a.next_action[(size_t)b * A + c];
+        nq += a.q_next_target[base + (size_t)c * N + n] * (staged ? s_nact[c] : a.next_action[(size_t)b * A + c]);
     }
     tq[n] = rew + disc * nd * nq;                                       // :142
     float cur = 0.f;                                                    // :149
     for (int c = 0; c < A; ++c) {
-      const float w = a.action[(size_t)b * A + c];
+      const float w = staged ? s_act[c] : a.action[(size_t)b * A + c];
       if (w != 0.f) cur += a.q_cur[base + (size_t)c * N + n] * w;
     }
     cq[n] = cur;
@@ -188,23 +194,41 @@ __global__ void __launch_bounds__(256) qr_head_kernel(const QrDev d) {
     const float c = cq[j];
     const float tau = (0.5f + (float)j) / (float)N;   // :70-73
     float g = 0.f;
-    for (int i = 0; i < N; ++i) {
-      const float td = tq[i] - c;
-      const float ad = fabsf(td);
-      const float w = fabsf(tau - (td < 0.f ? 1.f : 0.f));
-      lsum += (ad < 1.f ? 0.5f * td * td : ad - 0.5f) * w;              // huber (:217-218)
-      g += (ad < 1.f ? td : (td > 0.f ? 1.f : -1.f)) * w;
+    // |tau - 1[td < 0]| takes two values; huber'(td) = clamp(td, -1, 1) =: gs and
+    // huber(td) = gs * (td - gs / 2) (= td^2 / 2 inside, |td| - 1/2 outside: the same roundings
+    // as the two-branch form, multiplication by 1/2 being exact)
+    const float w_neg = fabsf(tau - 1.f), w_pos = fabsf(tau);
+    float l2 = 0.f, g2 = 0.f;  // second accumulators: two independent dependency chains
+    int i = 0;
+    for (; i + 1 < N; i += 2) {
+      const float td0 = tq[i] - c, td1 = tq[i + 1] - c;
+      const float gs0 = fmaxf(-1.f, fminf(1.f, td0)), gs1 = fmaxf(-1.f, fminf(1.f, td1));
+      const float w0 = td0 < 0.f ? w_neg : w_pos, w1 = td1 < 0.f ? w_neg : w_pos;
+      lsum += (gs0 * (td0 - 0.5f * gs0)) * w0;                          // huber (:217-218)
+      l2 += (gs1 * (td1 - 0.5f * gs1)) * w1;
+      g += gs0 * w0;
+      g2 += gs1 * w1;
     }
+    if (i < N) {
+      const float td0 = tq[i] - c;
+      const float gs0 = fmaxf(-1.f, fminf(1.f, td0));
+      const float w0 = td0 < 0.f ? w_neg : w_pos;
+      lsum += (gs0 * (td0 - 0.5f * gs0)) * w0;
+      g += gs0 * w0;
+    }
+    lsum += l2;
+    g += g2;
     const float dcur = -g * norm;   // d loss / d current[j]
     // d loss / d head output [b, a, j] = action[b,a] * dcur  (linear head)
     for (int cact = 0; cact < A; ++cact)
-      a.dz_head[base + (size_t)cact * N + j] = a.action[(size_t)b * A + cact] * dcur;
+      a.dz_head[base + (size_t)cact * N + j] = (staged ? s_act[cact] : a.action[(size_t)b * A + cact]) * dcur;
   }
-  red[tid] = lsum;
+  lsum = warp_sum(lsum);
+  if ((tid & 31) == 0) red[tid >> 5] = lsum;
   __syncthreads();
   if (tid == 0) {
     float s = 0.f;
-    for (int i = 0; i < (int)blockDim.x; ++i) s += red[i];
+    for (int i = 0; i < (int)blockDim.x / 32; ++i) s += red[i];
     a.loss_partials[b] = s;
     __threadfence();
     const unsigned done = atomicAdd(a.tile_counter, 1u);

@@ -38,6 +38,9 @@ constexpr int kTcIters = kTcM * (kTcKC / 4) / kTcThreads;  // 16 B pieces per th
 struct TcDev {
   const float* in; const float* W; const float* b; float* out;
   int batch, K, N, act;
+  // split-K (blockIdx.z): slice z walks chunks [z * chunks_per_split, ...) and stores its RAW
+  // partial tile (no bias / activation) to out + z * batch * N; 0 = no split
+  int chunks_per_split;
 };
 
 __global__ void __launch_bounds__(kTcThreads, 3) tc_linear_fwd_kernel(const TcDev p) {
@@ -53,7 +56,13 @@ __global__ void __launch_bounds__(kTcThreads, 3) tc_linear_fwd_kernel(const TcDe
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * kTcM, col0 = blockIdx.y * kTcN;
   const int K = p.K;
-  const int nchunks = ceil_div(K, kTcKC);
+  int c_begin = 0, nchunks = ceil_div(K, kTcKC);
+  const bool raw = p.chunks_per_split > 0;
+  if (raw) {
+    c_begin = (int)blockIdx.z * p.chunks_per_split;
+    nchunks = nchunks < c_begin + p.chunks_per_split ? nchunks : c_begin + p.chunks_per_split;
+  }
+  float* const outp = raw ? p.out + (size_t)blockIdx.z * p.batch * p.N : p.out;
   const bool vin = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0);
   const bool vw = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0);
 
@@ -111,10 +120,10 @@ __global__ void __launch_bounds__(kTcThreads, 3) tc_linear_fwd_kernel(const TcDe
     }
   };
 
-  load_regs(0);
-  for (int c = 0; c < nchunks; ++c) {
+  load_regs(c_begin);
+  for (int c = c_begin; c < nchunks; ++c) {
     // the MMAs of the previous chunk must have consumed the stage
-    if (c > 0) mbar_wait(bar, (c - 1) & 1);
+    if (c > c_begin) mbar_wait(bar, (c - c_begin - 1) & 1);
 #pragma unroll
     for (int it = 0; it < kTcIters; ++it) {
       const int idx = tid + it * kTcThreads;
@@ -142,7 +151,7 @@ __global__ void __launch_bounds__(kTcThreads, 3) tc_linear_fwd_kernel(const TcDe
         const uint64_t dal = umma_desc(smem_u32(a_lo) + koff, LBO, SBO);
         const uint64_t dbh = umma_desc(smem_u32(b_hi) + koff, LBO, SBO);
         const uint64_t dbl = umma_desc(smem_u32(b_lo) + koff, LBO, SBO);
-        umma_tf32(tmem_d, dal, dbh, idesc, (c > 0 || s4 > 0) ? 1u : 0u);
+        umma_tf32(tmem_d, dal, dbh, idesc, (c > c_begin || s4 > 0) ? 1u : 0u);
         umma_tf32(tmem_d, dah, dbl, idesc, 1u);
         umma_tf32(tmem_d, dah, dbh, idesc, 1u);
       }
@@ -151,7 +160,7 @@ __global__ void __launch_bounds__(kTcThreads, 3) tc_linear_fwd_kernel(const TcDe
     // global loads of the next chunk fly while the tensor core works on this one
     if (c + 1 < nchunks) load_regs(c + 1);
   }
-  mbar_wait(bar, (nchunks - 1) & 1);
+  mbar_wait(bar, (nchunks - c_begin - 1) & 1);
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
 
   // ---- epilogue: TMEM -> registers -> bias + activation -> smem tile -> coalesced global ----
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(kTcThreads, 3) tc_linear_fwd_kernel(const TcDe
     }
     __syncthreads();
     // each warp writes whole 512-byte row segments; bias + activation applied on the way out
-    const bool vo = ((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    const bool vo = ((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(outp) & 15) == 0);
     for (int idx = tid; idx < kTcM * (kTcN / 4); idx += kTcThreads) {
       const int rr = idx >> 5, c4 = (idx & 31) * 4;
       const int row = row0 + rr, col = col0 + c4;
@@ -193,8 +202,8 @@ __global__ void __launch_bounds__(kTcThreads, 3) tc_linear_fwd_kernel(const TcDe
       float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (col + j < p.N) ov[j] = act_fwd(ov[j] + (p.b ? __ldg(p.b + col + j) : 0.f), p.act);
-      float* dst = p.out + (size_t)row * p.N + col;
+        if (!raw && col + j < p.N) ov[j] = act_fwd(ov[j] + (p.b ? __ldg(p.b + col + j) : 0.f), p.act);
+      float* dst = outp + (size_t)row * p.N + col;
       if (vo && col + 3 < p.N) {
         *reinterpret_cast<float4*>(dst) = make_float4(ov[0], ov[1], ov[2], ov[3]);
       } else {
@@ -211,9 +220,101 @@ __global__ void __launch_bounds__(kTcThreads, 3) tc_linear_fwd_kernel(const TcDe
   }
 }
 
+// ---- nn.Linear backward w.r.t. its input on the same kernel (split-K) ----------------------
+// Wt[k][n] = W[n][k]: the GEMM above wants both operands contiguous along the contraction
+__global__ void __launch_bounds__(256) tc_transpose_kernel(const float* __restrict__ W, int N, int K,
+                                                          float* __restrict__ Wt) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int n = n0 + j, k = k0 + tx;
+    tile[j][tx] = (n < N && k < K) ? W[(size_t)n * K + k] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int k = k0 + j, n = n0 + tx;
+    if (k < K && n < N) Wt[(size_t)k * N + n] = tile[tx][j];
+  }
+}
+
+// out[b][k] = (sum over slices of partial[s][b][k]) * act'(h_prev[b][k]), slices added in order
+__global__ void __launch_bounds__(256) tc_dx_reduce_kernel(const float* __restrict__ partial, int splits,
+                                                          size_t slice, const float* __restrict__ h_prev,
+                                                          int act_prev, float* __restrict__ out, size_t n4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 acc = reinterpret_cast<const float4*>(partial)[i];
+  for (int s = 1; s < splits; ++s) {
+    const float4 v = reinterpret_cast<const float4*>(partial + (size_t)s * slice)[i];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  if (h_prev && act_prev != RB200_ACT_LINEAR) {
+    const float4 h = reinterpret_cast<const float4*>(h_prev)[i];
+    acc.x *= act_bwd_from_out(h.x, act_prev); acc.y *= act_bwd_from_out(h.y, act_prev);
+    acc.z *= act_bwd_from_out(h.z, act_prev); acc.w *= act_bwd_from_out(h.w, act_prev);
+  }
+  reinterpret_cast<float4*>(out)[i] = acc;
+}
+
+struct DxPlan { int splits, chunks_per_split; size_t wt_floats, partial_floats; };
+// the tcgen05 path pays off for a wide layer (N = out features is the contraction here)
+static bool dx_plan(int K, int N, int batch, DxPlan* pl) {
+  if (N < 1024 || batch < 256 || (K & 3) != 0 || (N & 3) != 0) return false;
+  const int tiles = ceil_div(batch, kTcM) * ceil_div(K, kTcN);
+  const int nchunks = ceil_div(N, kTcKC);
+  int splits = (3 * 148) / tiles;  // three CTAs per SM
+  splits = splits < 1 ? 1 : (splits > nchunks ? nchunks : splits);
+  pl->chunks_per_split = ceil_div(nchunks, splits);
+  pl->splits = ceil_div(nchunks, pl->chunks_per_split);
+  pl->wt_floats = ((size_t)K * N + 31) & ~(size_t)31;
+  pl->partial_floats = (size_t)pl->splits * batch * K;
+  return true;
+}
+
 }  // namespace rb200
 
 using namespace rb200;
+
+// Scratch bytes rb200_linear_backward_dx_tc needs for this shape; 0 = shape not taken by the
+// tcgen05 path (use rb200_linear_backward_dx).
+extern "C" int64_t rb200_linear_backward_dx_tc_scratch_bytes(int32_t K, int32_t N, int32_t batch) {
+  DxPlan pl;
+  if (K <= 0 || N <= 0 || batch <= 0 || !dx_plan(K, N, batch, &pl)) return 0;
+  return (int64_t)((pl.wt_floats + pl.partial_floats) * sizeof(float));
+}
+
+// Same contract as rb200_linear_backward_dx (W is the nn.Linear weight [N out x K in], dz [B, N],
+// out [B, K] = (dz . W) * act'(h_prev)) on tcgen05: W is transposed into the scratch, the
+// contraction over N runs as split-K slices of tc_linear_fwd_kernel, a last pass adds the
+// slices in order and applies act'.
+extern "C" int rb200_linear_backward_dx_tc(const float* W, int32_t K, int32_t N, const float* dz,
+                                           const float* h_prev, int32_t act_prev, int32_t batch,
+                                           float* out, void* scratch, int64_t scratch_bytes,
+                                           void* stream) {
+  if (!W || !dz || !out || !scratch || K <= 0 || N <= 0 || batch <= 0) { set_last_error("rb200_linear_backward_dx_tc: bad argument"); return RB200_E_INVALID; }
+  DxPlan pl;
+  if (!dx_plan(K, N, batch, &pl)) { set_last_error("rb200_linear_backward_dx_tc: shape not supported (N >= 1024, batch >= 256, K and N multiples of 4)"); return RB200_E_INVALID; }
+  if (scratch_bytes < (int64_t)((pl.wt_floats + pl.partial_floats) * sizeof(float))) { set_last_error("rb200_linear_backward_dx_tc: scratch too small"); return RB200_E_INVALID; }
+  if ((reinterpret_cast<uintptr_t>(scratch) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (h_prev && (reinterpret_cast<uintptr_t>(h_prev) & 15))) { set_last_error("rb200_linear_backward_dx_tc: buffers must be 16-byte aligned"); return RB200_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  static SmemOptIn optin = {};
+  {
+    cudaError_t e = ensure_dynamic_smem(tc_linear_fwd_kernel, optin, (size_t)kTcSmemBytes);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tc_linear_fwd)");
+  }
+  float* Wt = static_cast<float*>(scratch);
+  float* partial = Wt + pl.wt_floats;
+  tc_transpose_kernel<<<dim3(ceil_div(N, 32), ceil_div(K, 32)), 256, 0, st>>>(W, N, K, Wt);
+  TcDev p{dz, Wt, nullptr, partial, batch, /*contraction*/ N, /*columns*/ K, RB200_ACT_LINEAR, pl.chunks_per_split};
+  dim3 grid(ceil_div(batch, kTcM), ceil_div(K, kTcN), pl.splits);
+  tc_linear_fwd_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(p);
+  const size_t n4 = (size_t)batch * K / 4;
+  tc_dx_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(partial, pl.splits, (size_t)batch * K, h_prev,
+                                                                   act_prev, out, n4);
+  return check_cuda(cudaGetLastError(), "rb200_linear_backward_dx_tc launch");
+}
 
 // Same contract as rb200_linear_forward; chosen by it for large shapes.
 extern "C" int rb200_linear_forward_tc(const float* W, const float* b, int32_t act, int32_t K,
@@ -225,7 +326,7 @@ extern "C" int rb200_linear_forward_tc(const float* W, const float* b, int32_t a
     cudaError_t e = ensure_dynamic_smem(tc_linear_fwd_kernel, optin, (size_t)kTcSmemBytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tc_linear_fwd)");
   }
-  TcDev p{in, W, b, out, batch, K, N, act};
+  TcDev p{in, W, b, out, batch, K, N, act, 0};
   dim3 grid(ceil_div(batch, kTcM), ceil_div(N, kTcN));
   tc_linear_fwd_kernel<<<grid, kTcThreads, kTcSmemBytes, (cudaStream_t)stream>>>(p);
   return check_cuda(cudaGetLastError(), "tc_linear_fwd_kernel launch");

@@ -12,7 +12,7 @@ from ..core.parameters import RLParameters
 from ..optimizer import Optimizer__Union, SoftUpdate
 from .reagent_lightning_module import ReAgentLightningModule
 from .rl_trainer_pytorch import RLTrainerMixin
-from .workspace import NetWorkspace, param_grads, wgrad
+from .workspace import NetWorkspace, head_backward_dx, param_grads, wgrad
 
 
 def _f32c(t):
@@ -143,11 +143,7 @@ class C51Trainer(RLTrainerMixin, ReAgentLightningModule):
         a.tile_counter = ws["counter"].data_ptr()
         _lib.check(lib.rb200_c51_head(a, st), "rb200_c51_head")
         if L > 1:
-            f = qa.flat.data_ptr()
-            rc = lib.rb200_linear_backward_dx(
-                f + 4 * qa.w_off[L - 1], qa.dims[L - 1], qa.dims[L], ws["net"].dz[L - 1].data_ptr(),
-                ws["net"].hidden[L - 2].data_ptr(), qa.acts[L - 2], B, ws["net"].dz[L - 2].data_ptr(), st)
-            _lib.check(rc, "rb200_linear_backward_dx")
+            head_backward_dx(qa, ws["net"], B, ws)
             if L > 2:
                 rc = lib.rb200_mlp_backward(qa.desc(L - 1), ws["net"].dz[L - 2].data_ptr(), B, ws["net"].c, st)
                 _lib.check(rc, "rb200_mlp_backward")

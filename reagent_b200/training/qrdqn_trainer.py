@@ -19,7 +19,7 @@ from ..core.parameters import EvaluationParameters, RLParameters
 from ..optimizer import Optimizer__Union, SoftUpdate
 from .dqn_trainer import _f32c
 from .dqn_trainer_base import DQNTrainerBaseLightning
-from .workspace import NetWorkspace, param_grads, wgrad
+from .workspace import NetWorkspace, head_backward_dx, param_grads, wgrad
 
 
 class QRDQNTrainer(DQNTrainerBaseLightning):
@@ -169,12 +169,7 @@ class QRDQNTrainer(DQNTrainerBaseLightning):
         a.tile_counter = ws["counter"].data_ptr()
         _lib.check(lib.rb200_qrdqn_head(a, st), "rb200_qrdqn_head")
         if L > 1:
-            flat = qa.flat
-            rc = lib.rb200_linear_backward_dx(
-                flat.data_ptr() + 4 * qa.w_off[L - 1], qa.dims[L - 1], qa.dims[L],
-                ws["net"].dz[L - 1].data_ptr(), ws["net"].hidden[L - 2].data_ptr(),
-                qa.acts[L - 2], B, ws["net"].dz[L - 2].data_ptr(), st)
-            _lib.check(rc, "rb200_linear_backward_dx")
+            head_backward_dx(qa, ws["net"], B, ws)
             if L > 2:
                 rc = lib.rb200_mlp_backward(qa.desc(L - 1), ws["net"].dz[L - 2].data_ptr(), B,
                                             ws["net"].c, st)
