@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(256) c51_head_kernel(const C51Dev d) {
     }
   }
   __shared__ float s_l[8];
+  __shared__ bool s_last;
   le = warp_sum(le);
   if ((tid & 31) == 0) s_l[tid >> 5] = le;
   __syncthreads();
@@ -218,11 +219,24 @@ __global__ void __launch_bounds__(256) c51_head_kernel(const C51Dev d) {
     a.loss_partials[b] = t;
     __threadfence();
     const unsigned fin = atomicAdd(a.tile_counter, 1u);
-    if (fin == gridDim.x - 1) {
-      __threadfence();
-      float tot = 0.f;
-      for (unsigned i = 0; i < gridDim.x; ++i) tot += ((volatile float*)a.loss_partials)[i];
-      *a.loss = tot * invB;
+    s_last = fin == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    // one CTA per row: the last one adds the per-row partials with all its threads (thread t
+    // takes rows t, t + blockDim, ...; fixed combination order) instead of one thread walking
+    // `batch` dependent loads at the tail of the kernel
+    __threadfence();
+    float tot = 0.f;
+    for (unsigned i = tid; i < gridDim.x; i += blockDim.x) tot += ((volatile float*)a.loss_partials)[i];
+    tot = warp_sum(tot);
+    __syncthreads();
+    if ((tid & 31) == 0) s_l[tid >> 5] = tot;
+    __syncthreads();
+    if (tid == 0) {
+      float t2 = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t2 += s_l[w];
+      *a.loss = t2 * invB;
       *a.tile_counter = 0u;
     }
   }

@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(256) qr_head_kernel(const QrDev d) {
   float* means = cq + N;     // [A]
   float* red = means + A;    // [256]
   __shared__ int s_best;
-  __shared__ float s_act[64], s_nact[64];  // action / next_action weights of this row (A <= 64 staged)
+  __shared__ float s_act[64], s_nact[64], s_mask[64];  // per-row action weights / mask (A <= 64 staged)
+  __shared__ bool s_last;
   const int b = blockIdx.x, tid = threadIdx.x;
   const size_t base = (size_t)b * A * N;
 
@@ -136,14 +137,26 @@ __global__ void __launch_bounds__(256) qr_head_kernel(const QrDev d) {
   if (staged && tid < A) {
     s_act[tid] = a.action[(size_t)b * A + tid];
     s_nact[tid] = (!a.maxq && a.next_action) ? a.next_action[(size_t)b * A + tid] : 0.f;
+    s_mask[tid] = a.possible_next_actions_mask ? a.possible_next_actions_mask[(size_t)b * A + tid] : 1.f;
   }
   // mean over atoms of the selection network (qrdqn_trainer.py:127-133)
   const float* sel = a.double_q ? a.q_next_online : a.q_next_target;
-  for (int act = tid >> 5; act < A; act += 8) {
+  // (16-byte loads when the rows allow it: lane sums differ from the scalar path only in order)
+  const bool vec4 = (N & 3) == 0 && (reinterpret_cast<uintptr_t>(sel) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a.q_cur) & 15) == 0;
+  auto row_mean = [&](const float* src, int act) {
     float s = 0.f;
-    for (int n = tid & 31; n < N; n += 32) s += sel[base + (size_t)act * N + n];
-    s = warp_sum(s);
-    if ((tid & 31) == 0) means[act] = s / (float)N;
+    if (vec4) {
+      const float4* r4 = reinterpret_cast<const float4*>(src + base + (size_t)act * N);
+      for (int n = tid & 31; n < N / 4; n += 32) { const float4 v = __ldg(r4 + n); s += (v.x + v.y) + (v.z + v.w); }
+    } else {
+      for (int n = tid & 31; n < N; n += 32) s += src[base + (size_t)act * N + n];
+    }
+    return warp_sum(s) / (float)N;
+  };
+  for (int act = tid >> 5; act < A; act += 8) {
+    const float m = row_mean(sel, act);
+    if ((tid & 31) == 0) means[act] = m;
   }
   __syncthreads();
   if (tid == 0) {
@@ -152,7 +165,8 @@ __global__ void __launch_bounds__(256) qr_head_kernel(const QrDev d) {
       float best = 0.f;
       bi = -1;
       for (int c = 0; c < A; ++c) {
-        const float m = a.possible_next_actions_mask ? a.possible_next_actions_mask[(size_t)b * A + c] : 1.f;
+        const float m = staged ? s_mask[c]
+                               : (a.possible_next_actions_mask ? a.possible_next_actions_mask[(size_t)b * A + c] : 1.f);
         const float v = means[c] + -1e9f * (1.f - m);
         if (bi < 0 || v > best) { best = v; bi = c; }
       }
@@ -232,21 +246,32 @@ __global__ void __launch_bounds__(256) qr_head_kernel(const QrDev d) {
     a.loss_partials[b] = s;
     __threadfence();
     const unsigned done = atomicAdd(a.tile_counter, 1u);
-    if (done == gridDim.x - 1) {
-      __threadfence();
-      float tot = 0.f;
-      for (unsigned i = 0; i < gridDim.x; ++i) tot += ((volatile float*)a.loss_partials)[i];
-      *a.loss = tot * norm;
+    s_last = done == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    // the last row's CTA adds the per-row partials: thread t takes rows t, t + 256, ... and the
+    // block combines them in a fixed order (deterministic, and off one thread's critical path:
+    // 4096 dependent loads by a single thread were ~20 us of kernel tail)
+    __threadfence();
+    float tot = 0.f;
+    for (unsigned i = tid; i < gridDim.x; i += blockDim.x) tot += ((volatile float*)a.loss_partials)[i];
+    tot = warp_sum(tot);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = tot;
+    __syncthreads();
+    if (tid == 0) {
+      float t2 = 0.f;
+      for (int i = 0; i < (int)blockDim.x / 32; ++i) t2 += red[i];
+      *a.loss = t2 * norm;
       *a.tile_counter = 0u;
     }
   }
   // mean over atoms of q(s) for reporting (all_q_values, :146)
   if (a.all_q_values) {
     for (int act = tid >> 5; act < A; act += 8) {
-      float s = 0.f;
-      for (int n = tid & 31; n < N; n += 32) s += a.q_cur[base + (size_t)act * N + n];
-      s = warp_sum(s);
-      if ((tid & 31) == 0) a.all_q_values[(size_t)b * A + act] = s / (float)N;
+      const float m = row_mean(a.q_cur, act);
+      if ((tid & 31) == 0) a.all_q_values[(size_t)b * A + act] = m;
     }
   }
 }
