@@ -749,7 +749,7 @@ def run_generic(env, args, cfg):
         durs = [a.elapsed_time(b) for a, b in trainer._kernel_events]
         kern_ms = sum(durs) / len(durs)
     trainer._kernel_events = None
-    nlaunch = {"qrdqn": 13, "sac": 12, "td3": 9}[cfg["algo"]]
+    nlaunch = {"qrdqn": 15, "sac": 12, "td3": 9}[cfg["algo"]]
     conf = base_config(cfg, world)
     detail = dict(value_path="K updates, eager launches, device-timed, query values resident in HBM",
                   final_loss=last_loss, rows_per_rank=Bl)
@@ -773,10 +773,11 @@ def run_generic(env, args, cfg):
             "pipe_used": "mma.sync m16n8k8 tf32, 3xTF32", "ncu_file": None}
     elif cfg["algo"] == "qrdqn":
         res["roofline_kernel"] = {
-            "kernel": "whole QR-DQN update (tc_linear_fwd_kernel head on tcgen05 x3, qr_head_kernel, "
-                      "linear_bwd_wide_kernel, wgrad_kernel, adam_soft_kernel)",
+            "kernel": "whole QR-DQN update (tc_linear_fwd_kernel on tcgen05: head forward x3 and the "
+                      "split-K head backward; qr_head_kernel, wgrad_kernel, adam_soft_kernel)",
             "flops": update_flops(cfg, Bl), "kernel_ms": dev_ms / K,
-            "pipe_used": "tcgen05 kind::tf32 (head forward) + mma.sync tf32 (backward)", "ncu_file": None}
+            "pipe_used": "tcgen05 kind::tf32 (head forward + head dX) + mma.sync tf32 (trunk, wgrad)",
+            "ncu_file": None}
     if check:
         res["dp_check"] = check
     return res

@@ -766,6 +766,8 @@ class ReplayBuffer:
                     pass
 
     def load(self, checkpoint_dir, suffix):
+        if getattr(self, "_device_resident", None) is not None:
+            raise RuntimeError("the buffer is device-resident: call DeviceReplay.sync_to_host() before load()")
         elems = self._return_checkpointable_elements()
         for attr in elems:
             filename = self._generate_filename(checkpoint_dir, attr, suffix)
@@ -785,3 +787,12 @@ class ReplayBuffer:
                         self.__dict__[attr] = np.load(infile, allow_pickle=False)
                     else:
                         self.__dict__[attr] = pickle.load(infile)
+        # The loaded arrays replace whatever was staged or mirrored on the device: drop the rows
+        # still in the pinned staging block (the store they would be flushed into was just
+        # overwritten) and rebuild the device-side validity / priority mirrors.
+        self._stage_n = 0
+        self._valid_dirty = []
+        self._valid_index_stale = True
+        if self._valid_dev is not None:
+            self._valid_dev.copy_(self._is_index_valid.to(torch.uint8))
+        self._post_add_batch()

@@ -102,6 +102,28 @@ class FusedDqnStep:
             slots = 2
         for i in range(slots):
             self.slots.append(self._capture(i))
+        self._param_versions = self._versions()
+
+    # -- parameters changed from outside (load_state_dict, manual edits) ----------------------
+    def _versions(self):
+        t = self.trainer
+        return tuple(p._version for p in t.q_network.parameters()) + tuple(
+            p._version for p in t.q_network_target.parameters())
+
+    def invalidate_tc_images(self):
+        """The captured update keeps the tensor-core weight images of K2 current by itself (the
+        Adam kernel rewrites them).  If the parameters of q_network / q_network_target are
+        changed OUTSIDE this object, the images must be rebuilt before the next replay: writes
+        through torch (load_state_dict, `p.copy_`, ...) are detected by `step()`; call this
+        after anything torch's version counters cannot see (a raw kernel writing the arena)."""
+        self._param_versions = None
+
+    def _refresh_tc_images(self):
+        v = self._versions()
+        if v != self._param_versions:
+            self.trainer._tc_images_state = None
+            self.trainer.tc_prepack()  # eager, on the current stream, before the replay
+            self._param_versions = v
 
     # -- one update on the current stream ---------------------------------------
     def _one_update(self, rnd_dev):
@@ -227,6 +249,7 @@ class FusedDqnStep:
         self.k += 1
         if s["used"]:
             s["done"].synchronize()
+        self._refresh_tc_images()
         if self.dr is not None:
             if self._status_np[0] != 0:  # sticky device status of an earlier step
                 self.dr.raise_if_failed(self._status_host)

@@ -76,3 +76,34 @@ def test_fused_step_matches_eager(prioritized, prefetch):
         assert torch.equal(a, b)
     for a, b in zip(t.q_network_target.parameters(), t2.q_network_target.parameters()):
         assert torch.equal(a, b)
+
+
+def test_fused_step_sees_parameters_loaded_from_outside():
+    """load_state_dict between two replays of the captured update: the tensor-core weight
+    images of K2 are rebuilt before the next replay (FusedDqnStep._refresh_tc_images), so the
+    captured path keeps matching the eager one bit for bit."""
+    from reagent_b200.models import FullyConnectedDQN
+    from reagent_b200.training.fused_step import FusedDqnStep
+
+    torch.manual_seed(99)
+    donor = FullyConnectedDQN(S, A, [48, 32], ["relu", "relu"]).state_dict()
+    rb, t = _setup(True)
+    _seed()
+    eager = []
+    for i in range(6):
+        if i == 3:
+            t.q_network.load_state_dict(donor)
+        eager.append(float(t.train_batch(rb.sample_discrete_dqn_batch(B, A))))
+    rb2, t2 = _setup(True)
+    _seed()
+    fused = FusedDqnStep(t2, rb2, B, prefetch=False)
+    got = []
+    for i in range(1, 6):
+        if i == 3:
+            t2.q_network.load_state_dict(donor)
+        lh = fused.step()
+        torch.cuda.synchronize()
+        got.append(float(lh[0]))
+    assert got == eager[1:], (got, eager[1:])
+    for a, b in zip(t.q_network.parameters(), t2.q_network.parameters()):
+        assert torch.equal(a, b)

@@ -165,3 +165,39 @@ def test_preprocessor_matches_reference():
     # training mode range check (preprocessor.py:576-599): PROBABILITY stays within range
     p.train()
     p(x, pres)
+
+
+@pytest.mark.parametrize("name", ["replay_uniform_h3_wrap", "replay_per_h3_wrap_zero"])
+def test_checkpoint_load_rebuilds_device_mirrors(name, tmp_path):
+    """save() / load() (circular_replay_buffer.py:810-897 of the reference): loading into a
+    buffer whose device store, priority mirror and pinned staging block hold OTHER data must
+    leave it sampling exactly like the buffer that was saved."""
+    arrays, meta = G.load(name)
+    src = _build(arrays, meta, bulk=True)
+    src.save(str(tmp_path), 3)
+
+    # same add history (validity bookkeeping is private state and, as in the reference, not
+    # part of a checkpoint), different contents
+    other = {k: np.array(v, copy=True) for k, v in arrays.items()}
+    rng = np.random.RandomState(5)
+    for k in meta["keys"]:
+        v = other[f"stream.{k}"]
+        if k == "terminal":
+            continue
+        if k == "priority":
+            other[f"stream.{k}"] = rng.uniform(0.5, 2.0, v.shape)
+        elif np.issubdtype(v.dtype, np.floating):
+            other[f"stream.{k}"] = rng.standard_normal(v.shape).astype(v.dtype)
+    dst = _build(other, meta, bulk=True)
+    B = meta["B"]
+    random.seed(3); np.random.seed(3); torch.manual_seed(3)
+    dst.sample_transition_batch(batch_size=B)  # device mirrors of the OLD contents now exist
+    dst.load(str(tmp_path), 3)
+    assert dst._stage_n == 0
+
+    for rb in (src, dst):
+        random.seed(11); np.random.seed(11); torch.manual_seed(11)
+        rb._out = rb.sample_transition_batch(batch_size=B)
+    for f in src._out._fields:
+        a, b = getattr(src._out, f), getattr(dst._out, f)
+        assert torch.equal(torch.as_tensor(a).cpu(), torch.as_tensor(b).cpu()), f
