@@ -143,6 +143,13 @@ class DQNTrainer(DQNTrainerBaseLightning):
                 id(ta.flat), ta.flat._version, getattr(ta, "data_epoch", 0),
                 tuple(p._version for p in self.q_network_target.parameters()))
 
+    def invalidate_tc_images(self):
+        """Force the next TD step to rebuild the tensor-core weight images.  Needed only after a
+        parameter write that torch's version counters do not record (`p.data.copy_()`, a foreign
+        kernel writing into the arena); `load_state_dict`, optimizer steps and `p.copy_()` are
+        detected through `_tc_state()`."""
+        self._tc_images_state = None
+
     def _tc_images_current(self) -> bool:
         return self.__dict__.get("_tc_images_state") == self._tc_state()
 
