@@ -12,15 +12,16 @@
 //   weights      pre-tiled once per update (by the Adam kernel, or dqn_tc_pack_kernel) into one
 //                fp32 image per (128-feature tile, 32-k chunk) -- [k/4][row][4 floats].  The TD
 //                kernel streams the images through a shared-memory ring with 1-D bulk copies
-//                (cp.async.bulk -> mbarrier complete_tx, producer warp); FOUR LOADER WARPS (one
-//                per TMEM lane quadrant; a thread owns one weight row) read "my row" with
-//                conflict-free 16-byte loads, split it into TF32 hi / lo in registers and store
-//                both into a ring of TENSOR MEMORY columns (tcgen05.st): the weights are the
-//                A operand of the MMAs FROM TENSOR MEMORY.  Every weight byte therefore crosses
-//                shared memory once in and once out as raw fp32 (8 B per parameter) instead of
-//                hi+lo in and hi+lo out through the MMA (16 B): the shared-memory data pipe,
-//                which bounded the previous version (77 KB per chunk at 128 B/clk), carries
-//                45 KB per chunk, and the MMAs read only the small B operand from it.
+//                (cp.async.bulk -> mbarrier complete_tx, producer warp; a stage = two chunk
+//                images); FOUR LOADER WARPS (one per TMEM lane quadrant; a thread owns one weight
+//                row) read "my row" with conflict-free 16-byte loads, split it into TF32 hi / lo
+//                in registers and store both into a ring of TENSOR MEMORY columns (tcgen05.st):
+//                the weights are the A operand of the MMAs FROM TENSOR MEMORY.  Measured on B200
+//                (profiles/r02_summary.md): with A in tensor memory an MMA costs exactly its
+//                math (N/2 cycles at M = 128, K = 8), with A in shared memory 39-48 cycles
+//                whatever N <= 64; every weight byte crosses shared memory once in and once out
+//                as raw fp32.  The step is bound by the latency of this producer -> loader ->
+//                MMA chain and of the layer hand-overs, not by any pipe.
 //   activations  live in shared memory as hi/lo planes in the same canonical layout (rows =
 //                batch rows); the epilogue of layer l (tcgen05.ld -> bias -> activation -> split)
 //                writes them straight into the B operand of layer l+1 and, for the online
